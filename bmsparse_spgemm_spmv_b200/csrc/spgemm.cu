@@ -1,0 +1,540 @@
+// spgemm.cu -- C = A * B on the bmSparse form (A plain fp16, B in transposed-operand form fp16, C plain fp32).
+//
+// Replaces bmSparse_mult (src/bmSparse_SPGEMM.cu:827-1223).  The reference materialises every candidate
+// (A-block, B-block) pair as a 16-byte task (T_3), filters them with 64 AND-tests each (T_4), sorts the
+// survivors by C key with an indirect comparator or bb_segsort (T_5), and runs ~20 thrust passes over
+// the task list before its numeric kernel.  Here nothing is materialised and nothing is sorted:
+//
+//   row-wise (Gustavson) over A's block rows, one CTA per block row (dynamic queue), three passes
+//     COUNT   survivors of the 1-byte inner-dimension test (kmask_a & kmask_b) set a bit in a per-row
+//             bit set over C's block columns            -> C blocks per block row  (T_1..T_4)
+//     FILL    same bit set, ranked by a popc prefix: the rank of column j IS its sorted position, so
+//             C.keys come out ascending without a sort (replaces T_5/T_6 and bb_segsort); the
+//             boolean 8x8 product of the operand bitmaps is OR-ed into the block's bitmap   (T_9)
+//     NUMERIC bit set rebuilt from C.keys; every surviving pair is multiplied (scalar path for sparse
+//             blocks, mma.sync m16n8k8 fp16->fp32 path for dense blocks, two B blocks per MMA) and
+//             accumulated in shared memory, then stored coalesced                           (T_7)
+//   block rows whose bit set / block list / value list exceed the shared-memory caps run the same
+//   code on global scratch.
+#include "common.cuh"
+#include <vector>
+#include <algorithm>
+
+namespace bmsp {
+
+enum { PASS_COUNT = 0, PASS_FILL = 1, PASS_NUMERIC = 2 };
+enum { MODE_SETBITS = 0, MODE_FILL = 1, MODE_NUMERIC = 2 };
+
+struct GemmArgs {
+    const int32_t* a_brp; const int32_t* a_bcol; const uint64_t* a_bmps; const uint8_t* a_kmask; const uint64_t* a_off; const __half* a_val;
+    const int32_t* b_brp; const int32_t* b_bcol; const uint64_t* b_bmps; const uint8_t* b_kmask; const uint64_t* b_off; const __half* b_val;
+    const int2* rowinfo;       // per A block row: x = first C block column of the bit set (multiple of 32), y = words
+    int32_t row_begin, row_end;
+    int32_t G;                 // lanes cooperating on one A block (power of two <= 32)
+    int32_t cap_words, cap_c, cap_nnz;
+    uint32_t* g_bitset; uint32_t* g_wrank; int32_t max_words;   // per-CTA global scratch for over-cap rows
+    int32_t* work_counter;
+    uint32_t* row_count;       // COUNT out: C blocks per row (indexed row - row_begin)
+    int32_t* maxes;            // [0] max words, [1] max C blocks per row, [2] max C values per row
+    const int32_t* c_brp;      // FILL/NUMERIC in: C block-row pointers (indexed row - row_begin)
+    uint64_t* c_keys; uint64_t* c_bmps;
+    const uint64_t* c_off; float* c_val;
+    unsigned long long* stats; // [0] candidate pairs, [1] surviving pairs (COUNT pass)
+};
+
+// boolean 8x8 product of an A bitmap (row-major) and a B bitmap in transposed-operand form:
+// bit (i,j) = (row i of A) & (byte j of Bt) != 0   -- bmp_calculator, SPGEMM.cu:787-810
+__device__ __forceinline__ uint64_t pair_bitmap(uint64_t a, uint64_t bt) {
+    const uint32_t bh = (uint32_t)(bt >> 32), bl = (uint32_t)bt;
+    uint64_t res = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t ai = (uint32_t)(a >> (56 - 8 * i)) & 0xFFu;
+        const uint32_t rep = ai * 0x01010101u;
+        const uint32_t th = rep & bh, tl = rep & bl;
+        // 1 in the low bit of every non-zero byte
+        const uint32_t nh = ((((th & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | th) & 0x80808080u) >> 7;
+        const uint32_t nl = ((((tl & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | tl) & 0x80808080u) >> 7;
+        // gather bits 24,16,8,0 into a nibble (bit 24 -> 3 ... bit 0 -> 0): partial products never collide
+        const uint32_t byte = ((((nh * 0x01020408u) >> 24) & 0xFu) << 4) | (((nl * 0x01020408u) >> 24) & 0xFu);
+        res |= (uint64_t)byte << (56 - 8 * i);
+    }
+    return res;
+}
+
+__device__ __forceinline__ int rank64(uint64_t bmp, int p) { return p == 0 ? 0 : __popcll(bmp >> (64 - p)); }
+
+__global__ void pair_bitmap_test_kernel(const uint64_t* a, const uint64_t* bt, uint64_t* out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pair_bitmap(a[i], bt[i]);
+}
+
+// P0: warp per A block row: candidate pairs, and the span [jmin, jmax] of C block columns.
+__global__ void __launch_bounds__(256) rowinfo_kernel(const int32_t* __restrict__ a_brp, const int32_t* __restrict__ a_bcol,
+                                                      const int32_t* __restrict__ b_brp, const int32_t* __restrict__ b_bcol,
+                                                      int row_begin, int row_end, int2* __restrict__ rowinfo,
+                                                      unsigned long long* __restrict__ cand, int* __restrict__ maxes) {
+    const int lane = threadIdx.x & 31;
+    const int row = row_begin + blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= row_end) return;
+    int jmin = 0x7FFFFFFF, jmax = -1;
+    unsigned long long c = 0;
+    for (int a = a_brp[row] + lane; a < a_brp[row + 1]; a += 32) {
+        const int k = a_bcol[a];
+        const int b0 = b_brp[k], b1 = b_brp[k + 1];
+        if (b1 > b0) {
+            c += (unsigned long long)(b1 - b0);
+            jmin = min(jmin, b_bcol[b0]);
+            jmax = max(jmax, b_bcol[b1 - 1]);
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, o));
+        jmax = max(jmax, __shfl_xor_sync(0xffffffffu, jmax, o));
+    }
+    if (lane == 0) {
+        int jbase = 0, words = 0;
+        if (jmax >= 0) { jbase = jmin & ~31; words = ((jmax - jbase) >> 5) + 1; }
+        rowinfo[row - row_begin] = make_int2(jbase, words);
+        cand[row - row_begin] = c;
+        atomicMax(maxes, words);
+    }
+}
+
+// CTA-wide exclusive scan over popc(bitset words) -> wrank (may be null); returns the total to every thread.
+__device__ __forceinline__ uint32_t rank_words(const uint32_t* bitset, uint32_t* wrank, int nwords, uint32_t* s_tmp) {
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (nwords + T - 1) / T;
+    const int w0 = min(tid * per, nwords), w1 = min(w0 + per, nwords);
+    uint32_t s = 0;
+    for (int w = w0; w < w1; w++) s += __popc(bitset[w]);
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_tmp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = lane < (T >> 5) ? s_tmp[lane] : 0, vi = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
+            if (lane >= o) vi += t;
+        }
+        s_tmp[lane] = vi - v;
+        if (lane == 31) s_tmp[32] = vi;
+    }
+    __syncthreads();
+    uint32_t run = s_tmp[wid] + inc - s;
+    if (wrank) for (int w = w0; w < w1; w++) { wrank[w] = run; run += __popc(bitset[w]); }
+    const uint32_t total = s_tmp[32];
+    __syncthreads();
+    return total;
+}
+
+// Per-row state shared by the enumeration modes.
+struct RowCtx {
+    int row, a0, a1, jbase, c0;
+    uint32_t* bitset; uint32_t* wrank;
+    uint64_t* cbmp;      // FILL: staging (shared or global C.bmps+c0); NUMERIC: shared copy or null
+    uint32_t* coff;      // NUMERIC: value offsets relative to the row, or null (global mode)
+    float* acc;          // NUMERIC: shared accumulators or null (global atomics)
+};
+
+template <int MODE>
+__device__ __forceinline__ void process_pair(const GemmArgs& g, const RowCtx& r, int a, int b) {
+    const uint64_t abmp = g.a_bmps[a], bbmp = g.b_bmps[b];
+    const int j = g.b_bcol[b] - r.jbase;
+    const uint32_t word = r.bitset[j >> 5];
+    const int c = (int)r.wrank[j >> 5] + __popc(word & ((1u << (j & 31)) - 1u));
+    if (MODE == MODE_FILL) {
+        atomicOr((unsigned long long*)&r.cbmp[c], (unsigned long long)pair_bitmap(abmp, bbmp));
+    } else {
+        const __half* av = g.a_val + g.a_off[a];
+        const __half* bv = g.b_val + g.b_off[b];
+        uint64_t cb; float* dst;
+        if (r.acc) { cb = r.cbmp[c]; dst = r.acc + r.coff[c]; }
+        else { cb = g.c_bmps[r.c0 + c]; dst = g.c_val + g.c_off[r.c0 + c]; }
+        uint64_t rem = abmp;
+        int ka = 0;
+        while (rem) {
+            const int p = __clzll((long long)rem);
+            rem &= ~(0x8000000000000000ull >> p);
+            const int rr = p >> 3, k = p & 7;
+            const float aval = __half2float(av[ka++]);
+            uint64_t hits = bbmp & (0x8080808080808080ull >> k);    // B(k, c) for c = 0..7 (Bt cell = c*8+k)
+            while (hits) {
+                const int q = __clzll((long long)hits);
+                hits &= ~(0x8000000000000000ull >> q);
+                const float bval = __half2float(bv[rank64(bbmp, q)]);
+                atomicAdd(dst + rank64(cb, rr * 8 + (q >> 3)), aval * bval);
+            }
+        }
+    }
+}
+
+// Walk the row's candidate pairs: `slots` A blocks at a time, G lanes per A block striding over the
+// B block row.  MODE_SETBITS marks C block columns; the other modes compact survivors through a
+// per-warp queue so that all 32 lanes work on surviving pairs.
+template <int MODE, bool STATS>
+__device__ __forceinline__ void enumerate_row(const GemmArgs& g, const RowCtx& r, uint2* q, unsigned long long& n_cand,
+                                              unsigned long long& n_surv) {
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+    const int Gs = g.G, slots = T / Gs, slot = tid / Gs, gl = tid % Gs;
+    int qn = 0;
+    const int niter = (r.a1 - r.a0 + slots - 1) / slots;
+    for (int itA = 0; itA < niter; itA++) {
+        const int a = r.a0 + itA * slots + slot;
+        int b0 = 0, b1 = 0; uint32_t am = 0;
+        if (a < r.a1) {
+            const int k = g.a_bcol[a];
+            b0 = g.b_brp[k]; b1 = g.b_brp[k + 1];
+            am = g.a_kmask[a];
+        }
+        int maxlen = b1 - b0;    // warp-uniform trip count (ballot below)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+        for (int off = 0; off < maxlen; off += Gs) {
+            const int b = b0 + off + gl;
+            const bool valid = b < b1;
+            const bool surv = valid && (am & g.b_kmask[b]) != 0;
+            if (STATS) { n_cand += valid; n_surv += surv; }
+            if (MODE == MODE_SETBITS) {
+                if (surv) { const int j = g.b_bcol[b] - r.jbase; atomicOr(&r.bitset[j >> 5], 1u << (j & 31)); }
+            } else {
+                const uint32_t m = __ballot_sync(0xffffffffu, surv);
+                if (surv) q[qn + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)a, (uint32_t)b);
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32) {
+                    const uint2 e = q[lane];
+                    uint2 t = make_uint2(0, 0);
+                    const bool mv = lane + 32 < qn;
+                    if (mv) t = q[32 + lane];
+                    __syncwarp();
+                    if (mv) q[lane] = t;
+                    qn -= 32;
+                    __syncwarp();
+                    process_pair<MODE>(g, r, (int)e.x, (int)e.y);
+                }
+            }
+        }
+    }
+    if (MODE != MODE_SETBITS) {
+        if (lane < qn) { const uint2 e = q[lane]; process_pair<MODE>(g, r, (int)e.x, (int)e.y); }
+        __syncwarp();
+    }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256) spgemm_pass_kernel(GemmArgs g) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = T >> 5;
+    // shared-memory carve-up (sizes mirrored by pass_smem_bytes on the host)
+    uint64_t* s_cbmp = reinterpret_cast<uint64_t*>(smem);                                        // [cap_c]     FILL, NUMERIC
+    uint2* s_queue = reinterpret_cast<uint2*>(s_cbmp + (PASS == PASS_COUNT ? 0 : g.cap_c));       // [nwarps*64] FILL, NUMERIC
+    uint32_t* s_bitset = reinterpret_cast<uint32_t*>(s_queue + (PASS == PASS_COUNT ? 0 : nwarps * 64));   // [cap_words]
+    uint32_t* s_wrank = s_bitset + g.cap_words;                                                   // [cap_words] FILL, NUMERIC
+    uint32_t* s_coff = s_wrank + (PASS == PASS_COUNT ? 0 : g.cap_words);                          // [cap_c]     NUMERIC
+    float* s_acc = reinterpret_cast<float*>(s_coff + (PASS == PASS_NUMERIC ? g.cap_c : 0));       // [cap_nnz]   NUMERIC
+    uint32_t* s_tmp = reinterpret_cast<uint32_t*>(s_acc + (PASS == PASS_NUMERIC ? g.cap_nnz : 0)); // [34]
+    int* s_row = reinterpret_cast<int*>(s_tmp + 34);
+
+    unsigned long long n_cand = 0, n_surv = 0;
+    uint2* q = s_queue + wid * 64;
+
+    while (true) {
+        if (tid == 0) *s_row = g.row_begin + atomicAdd(g.work_counter, 1);
+        __syncthreads();
+        RowCtx r;
+        r.row = *s_row;
+        __syncthreads();
+        if (r.row >= g.row_end) break;
+        const int lrow = r.row - g.row_begin;
+        const int2 ri = g.rowinfo[lrow];
+        r.jbase = ri.x;
+        const int nwords = ri.y;
+        r.a0 = g.a_brp[r.row]; r.a1 = g.a_brp[r.row + 1];
+        if (nwords == 0) {
+            if (PASS == PASS_COUNT && tid == 0) g.row_count[lrow] = 0;
+            continue;
+        }
+        const bool wfit = nwords <= g.cap_words;
+        r.bitset = wfit ? s_bitset : g.g_bitset + (size_t)blockIdx.x * g.max_words;
+        r.wrank = wfit ? s_wrank : g.g_wrank + (size_t)blockIdx.x * g.max_words;
+        r.cbmp = nullptr; r.coff = nullptr; r.acc = nullptr; r.c0 = 0;
+        for (int w = tid; w < nwords; w += T) r.bitset[w] = 0;
+        int ccount = 0;
+        if (PASS != PASS_COUNT) { r.c0 = g.c_brp[lrow]; ccount = g.c_brp[lrow + 1] - r.c0; }
+        if (PASS != PASS_COUNT && ccount == 0) { __syncthreads(); continue; }
+
+        if (PASS == PASS_COUNT) {
+            __syncthreads();
+            enumerate_row<MODE_SETBITS, true>(g, r, q, n_cand, n_surv);
+            __syncthreads();
+            const uint32_t total = rank_words(r.bitset, nullptr, nwords, s_tmp);
+            if (tid == 0) { g.row_count[lrow] = total; atomicMax(g.maxes + 1, (int)total); }
+        }
+        if (PASS == PASS_FILL) {
+            const bool cfit = ccount <= g.cap_c;
+            r.cbmp = cfit ? s_cbmp : g.c_bmps + r.c0;          // global C.bmps is pre-zeroed
+            if (cfit) for (int c = tid; c < ccount; c += T) r.cbmp[c] = 0;
+            __syncthreads();
+            enumerate_row<MODE_SETBITS, false>(g, r, q, n_cand, n_surv);
+            __syncthreads();
+            rank_words(r.bitset, r.wrank, nwords, s_tmp);
+            enumerate_row<MODE_FILL, false>(g, r, q, n_cand, n_surv);
+            __syncthreads();
+            // keys + bitmaps out: ascending bit index = ascending block column
+            for (int w = tid; w < nwords; w += T) {
+                uint32_t word = r.bitset[w];
+                int c = (int)r.wrank[w];
+                while (word) {
+                    const int bit = __ffs(word) - 1;
+                    word &= word - 1;
+                    g.c_keys[r.c0 + c] = ((uint64_t)(uint32_t)r.row << 32) | (uint32_t)(r.jbase + w * 32 + bit);
+                    if (cfit) g.c_bmps[r.c0 + c] = r.cbmp[c];
+                    c++;
+                }
+            }
+        }
+        if (PASS == PASS_NUMERIC) {
+            const uint64_t vbase = g.c_off[r.c0];
+            const int64_t rownnz = (int64_t)(g.c_off[r.c0 + ccount] - vbase);
+            const bool fit = ccount <= g.cap_c && rownnz <= g.cap_nnz;
+            if (fit) {
+                r.cbmp = s_cbmp; r.coff = s_coff; r.acc = s_acc;
+                for (int c = tid; c < ccount; c += T) { s_cbmp[c] = g.c_bmps[r.c0 + c]; s_coff[c] = (uint32_t)(g.c_off[r.c0 + c] - vbase); }
+                for (int v = tid; v < rownnz; v += T) s_acc[v] = 0.f;
+            }
+            __syncthreads();
+            for (int c = tid; c < ccount; c += T) {       // bit set from C's own block columns
+                const int j = (int)(g.c_keys[r.c0 + c] & 0xFFFFFFFFull) - r.jbase;
+                atomicOr(&r.bitset[j >> 5], 1u << (j & 31));
+            }
+            __syncthreads();
+            rank_words(r.bitset, r.wrank, nwords, s_tmp);
+            enumerate_row<MODE_NUMERIC, false>(g, r, q, n_cand, n_surv);
+            __syncthreads();
+            if (fit) for (int v = tid; v < rownnz; v += T) g.c_val[vbase + v] = s_acc[v];
+        }
+        __syncthreads();
+    }
+    if (PASS == PASS_COUNT) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o); n_surv += __shfl_xor_sync(0xffffffffu, n_surv, o); }
+        if (lane == 0) { atomicAdd(g.stats, n_cand); atomicAdd(g.stats + 1, n_surv); }
+    }
+}
+
+static size_t pass_smem_bytes(int pass, int T, int cap_words, int cap_c, int cap_nnz) {
+    size_t s = 0;
+    if (pass != PASS_COUNT) s += (size_t)cap_c * 8 + (size_t)(T / 32) * 64 * 8;
+    s += (size_t)cap_words * 4;
+    if (pass != PASS_COUNT) s += (size_t)cap_words * 4;
+    if (pass == PASS_NUMERIC) s += (size_t)cap_c * 4 + (size_t)cap_nnz * 4;
+    s += 34 * 4 + 16;
+    return s;
+}
+
+__global__ void popc_kernel(const uint64_t* __restrict__ bmps, uint64_t* __restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint64_t)__popcll(bmps[i]);
+}
+__global__ void row_nnz_max_kernel(const int32_t* __restrict__ c_brp, const uint64_t* __restrict__ c_off, int nrows, int* __restrict__ maxes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    uint64_t n = c_off[c_brp[i + 1]] - c_off[c_brp[i]];
+    atomicMax(maxes + 2, (int)min(n, (uint64_t)0x7FFFFFFF));
+}
+
+}  // namespace bmsp
+
+using namespace bmsp;
+
+extern "C" int bmsp_debug_pair_bitmap(int64_t n, const uint64_t* a_host, const uint64_t* bt_host, uint64_t* out_host) {
+    uint64_t *a = nullptr, *b = nullptr, *o = nullptr;
+    cudaStream_t st = 0;
+    BMSP_TRY(dev_alloc_t(&a, (size_t)n, st)); BMSP_TRY(dev_alloc_t(&b, (size_t)n, st)); BMSP_TRY(dev_alloc_t(&o, (size_t)n, st));
+    BMSP_CUDA(cudaMemcpyAsync(a, a_host, 8 * n, cudaMemcpyHostToDevice, st));
+    BMSP_CUDA(cudaMemcpyAsync(b, bt_host, 8 * n, cudaMemcpyHostToDevice, st));
+    pair_bitmap_test_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(a, b, o, n);
+    BMSP_KERNEL_CHECK();
+    BMSP_CUDA(cudaMemcpyAsync(out_host, o, 8 * n, cudaMemcpyDeviceToHost, st));
+    BMSP_CUDA(cudaStreamSynchronize(st));
+    dev_free(a, st); dev_free(b, st); dev_free(o, st);
+    return BMSP_OK;
+}
+
+template <int PASS>
+static int launch_pass(GemmArgs& g, int T, int sms, cudaStream_t st, int* grid_out) {
+    const size_t smem = pass_smem_bytes(PASS, T, g.cap_words, g.cap_c, g.cap_nnz);
+    auto kern = spgemm_pass_kernel<PASS>;
+    BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    int occ = 0;
+    BMSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
+    if (occ < 1) { set_error("spgemm pass %d does not fit: smem %zu", PASS, smem); return BMSP_ERR_CUDA; }
+    int grid = std::min<int64_t>((int64_t)sms * occ, (int64_t)g.row_end - g.row_begin);
+    grid = std::max(grid, 1);
+    if (grid_out) *grid_out = sms * occ;
+    BMSP_CUDA(cudaMemsetAsync(g.work_counter, 0, sizeof(int32_t), st));
+    kern<<<grid, T, smem, st>>>(g);
+    BMSP_KERNEL_CHECK();
+    return BMSP_OK;
+}
+
+extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_opts* opts, void* stream, bmsp_matrix_t* Cout,
+                           bmsp_spgemm_info* info) {
+    if (!A || !Bt || !Cout) { set_error("bmsp_spgemm: null argument"); return BMSP_ERR_INVALID; }
+    if (A->transposed || !Bt->transposed) { set_error("bmsp_spgemm: A must be plain and B in transposed-operand form (SPGEMM.cu:1261-1262)"); return BMSP_ERR_INVALID; }
+    if (A->dtype != BMSP_F16 || Bt->dtype != BMSP_F16) { set_error("bmsp_spgemm: operands must be fp16 (bmSparse_mult<half,float>)"); return BMSP_ERR_UNSUPPORTED; }
+    if (A->cols != Bt->rows) { set_error("bmsp_spgemm: inner dimensions differ (%d vs %d)", A->cols, Bt->rows); return BMSP_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rb = 0, re = A->nbr;
+    if (opts && (opts->brow_begin != 0 || opts->brow_end != 0)) { rb = opts->brow_begin; re = opts->brow_end; }
+    if (rb < 0 || re > A->nbr || rb > re) { set_error("bmsp_spgemm: bad block-row range [%d,%d)", rb, re); return BMSP_ERR_INVALID; }
+    const int nrows = re - rb;
+    const bool verbose = opts && opts->verbose;
+
+    int dev = 0, sms = 0;
+    BMSP_CUDA(cudaGetDevice(&dev));
+    BMSP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (verbose) for (auto& e : ev) BMSP_CUDA(cudaEventCreate(&e));
+    if (verbose) BMSP_CUDA(cudaEventRecord(ev[0], st));
+
+    // ---- scratch
+    int2* rowinfo = nullptr; unsigned long long* cand = nullptr; int32_t* small = nullptr;   // small: maxes[3], counter, pad, stats[2]
+    uint32_t* row_count = nullptr;
+    bmsp_matrix_s* C = new bmsp_matrix_s();
+    C->rows = A->rows; C->cols = Bt->cols; C->dtype = BMSP_F32; C->transposed = 0;
+    uint32_t *g_bitset = nullptr, *g_wrank = nullptr;
+    int status = BMSP_OK;
+    auto cleanup = [&]() {
+        dev_free(rowinfo, st); dev_free(cand, st); dev_free(small, st); dev_free(row_count, st);
+        dev_free(g_bitset, st); dev_free(g_wrank, st);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+    };
+    auto fail = [&](int code) { cleanup(); bmsp_destroy(C); return code; };
+#define SG_TRY(x) do { status = (x); if (status != BMSP_OK) return fail(status); } while (0)
+#define SG_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return fail(cuda_fail(e__, #x, __FILE__, __LINE__)); } while (0)
+
+    SG_TRY(dev_alloc_t(&rowinfo, (size_t)nrows + 1, st));
+    SG_TRY(dev_alloc_t(&cand, (size_t)nrows + 1, st));
+    SG_TRY(dev_alloc_t(&small, 16, st));
+    SG_TRY(dev_alloc_t(&row_count, (size_t)nrows + 2, st));
+    SG_CUDA(cudaMemsetAsync(small, 0, 16 * sizeof(int32_t), st));
+    int32_t* maxes = small; int32_t* counter = small + 4; unsigned long long* stats = (unsigned long long*)(small + 8);
+
+    int32_t h_small[16] = {0};
+    if (nrows > 0) {
+        rowinfo_kernel<<<(unsigned)ceil_div(nrows, 8), 256, 0, st>>>(A->brp, A->bcol, Bt->brp, Bt->bcol, rb, re, rowinfo, cand, maxes);
+        SG_CUDA(cudaGetLastError());
+    }
+    SG_CUDA(cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    const int max_words = h_small[0];
+
+    // ---- launch shape from averages
+    const double avgB = Bt->nbr ? (double)Bt->nblk / Bt->nbr : 0.0;
+    const double avgA = A->nbr ? (double)A->nblk / A->nbr : 0.0;
+    int G = 1;
+    while (G < 32 && G < avgB) G <<= 1;
+    const double avg_cand = avgA * avgB;
+    const int T = avg_cand <= 96 ? 32 : (avg_cand <= 2048 ? 128 : 256);
+    if (G > T) G = T;
+
+    GemmArgs g;
+    g.a_brp = A->brp; g.a_bcol = A->bcol; g.a_bmps = A->bmps; g.a_kmask = A->kmask; g.a_off = A->offsets; g.a_val = (const __half*)A->values;
+    g.b_brp = Bt->brp; g.b_bcol = Bt->bcol; g.b_bmps = Bt->bmps; g.b_kmask = Bt->kmask; g.b_off = Bt->offsets; g.b_val = (const __half*)Bt->values;
+    g.rowinfo = rowinfo; g.row_begin = rb; g.row_end = re; g.G = G;
+    g.cap_words = std::max(1, std::min(max_words, 8192));
+    g.cap_c = 0; g.cap_nnz = 0;
+    g.g_bitset = nullptr; g.g_wrank = nullptr; g.max_words = max_words;
+    g.work_counter = counter; g.row_count = row_count; g.maxes = maxes;
+    g.c_brp = nullptr; g.c_keys = nullptr; g.c_bmps = nullptr; g.c_off = nullptr; g.c_val = nullptr; g.stats = stats;
+
+    if (max_words > g.cap_words) {
+        // over-cap rows use per-CTA global scratch; size it for the largest persistent grid (32 CTAs/SM)
+        const size_t n = (size_t)sms * 32 * max_words;
+        SG_TRY(dev_alloc_t(&g_bitset, n, st));
+        SG_TRY(dev_alloc_t(&g_wrank, n, st));
+        g.g_bitset = g_bitset; g.g_wrank = g_wrank;
+    }
+
+    // ---- COUNT
+    int64_t c_size = 0;
+    if (nrows > 0) {
+        SG_TRY(launch_pass<PASS_COUNT>(g, T, sms, st, nullptr));
+        SG_TRY(exclusive_scan_u32(row_count, row_count, nrows, st));
+        uint32_t tot = 0;
+        SG_CUDA(cudaMemcpyAsync(&tot, row_count + nrows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        c_size = tot;
+    }
+    if (c_size > 0x7FFFFFFFll) { set_error("C has %lld blocks (> 2^31-1)", (long long)c_size); return fail(BMSP_ERR_TOO_LARGE); }
+    const int max_c = h_small[1];
+    unsigned long long h_stats[2];
+    memcpy(h_stats, h_small + 8, sizeof(h_stats));
+
+    C->nblk = c_size; C->offsets_len = c_size + 1;
+    SG_TRY(dev_alloc_t(&C->keys, (size_t)c_size + 2, st));
+    SG_TRY(dev_alloc_t(&C->bmps, (size_t)c_size + 2, st));
+    SG_TRY(dev_alloc_t(&C->offsets, (size_t)c_size + 2, st));
+    g.c_brp = (const int32_t*)row_count; g.c_keys = C->keys; g.c_bmps = C->bmps;
+
+    // ---- FILL
+    g.cap_c = std::max(1, std::min(max_c, 4096));
+    if (c_size > 0) {
+        if (max_c > g.cap_c) SG_CUDA(cudaMemsetAsync(C->bmps, 0, sizeof(uint64_t) * c_size, st));
+        SG_TRY(launch_pass<PASS_FILL>(g, T, sms, st, nullptr));
+        popc_kernel<<<(unsigned)ceil_div(c_size, 256), 256, 0, st>>>(C->bmps, C->offsets, c_size);
+        SG_CUDA(cudaGetLastError());
+    }
+    SG_TRY(exclusive_scan_u64(C->offsets, C->offsets, c_size, st));
+    uint64_t c_nnz = 0;
+    if (nrows > 0 && c_size > 0) {
+        row_nnz_max_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>((const int32_t*)row_count, C->offsets, nrows, maxes);
+        SG_CUDA(cudaGetLastError());
+    }
+    SG_CUDA(cudaMemcpyAsync(&c_nnz, C->offsets + c_size, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    if (c_nnz > 0xFFFFFFFFull) { set_error("C has %llu values (> 2^32-1)", (unsigned long long)c_nnz); return fail(BMSP_ERR_TOO_LARGE); }
+    const int max_rownnz = h_small[2];
+    C->nnz = (int64_t)c_nnz;
+    SG_TRY(dev_alloc(&C->values, (size_t)c_nnz * 4 + 16, st));
+    if (verbose) SG_CUDA(cudaEventRecord(ev[1], st));
+
+    // ---- NUMERIC
+    g.c_off = C->offsets; g.c_val = (float*)C->values;
+    g.cap_nnz = std::max(1, std::min(max_rownnz, 12288));
+    if (c_nnz > 0) {
+        if (max_c > g.cap_c || max_rownnz > g.cap_nnz) SG_CUDA(cudaMemsetAsync(C->values, 0, (size_t)c_nnz * 4, st));
+        SG_TRY(launch_pass<PASS_NUMERIC>(g, T, sms, st, nullptr));
+    }
+    if (verbose) SG_CUDA(cudaEventRecord(ev[2], st));
+    SG_TRY(derive_compact(C, st));
+
+    if (info) {
+        memset(info, 0, sizeof(*info));
+        info->candidate_pairs = (int64_t)h_stats[0]; info->surviving_pairs = (int64_t)h_stats[1];
+        info->c_blocks = c_size; info->c_nnz = (int64_t)c_nnz; info->numeric_path = 0;
+        if (verbose) {
+            SG_CUDA(cudaEventSynchronize(ev[2]));
+            cudaEventElapsedTime(&info->symbolic_ms, ev[0], ev[1]);
+            cudaEventElapsedTime(&info->numeric_ms, ev[1], ev[2]);
+            info->total_ms = info->symbolic_ms + info->numeric_ms;
+        }
+    }
+    cleanup();
+    *Cout = C;
+    return BMSP_OK;
+#undef SG_TRY
+#undef SG_CUDA
+}
