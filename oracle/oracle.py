@@ -186,12 +186,12 @@ def csr_spgemm(a_rows, b_cols, a_rp, a_ci, a_v, b_rp, b_ci, b_v, drop_zeros=True
     return c_rp, c_ci[:nnz.value].copy(), c_v[:nnz.value].copy()
 
 
-def ref_csr_spmv(rows, cols, rp, ci, v, x) -> np.ndarray:
+def ref_csr_spmv(rows, cols, rp, ci, v, x, omp=False) -> np.ndarray:
     r = ref_lib()
     rp = np.ascontiguousarray(rp, np.int32); ci = np.ascontiguousarray(ci, np.int32)
     v = np.ascontiguousarray(v, np.float32); x = np.ascontiguousarray(x, np.float32)
     y = np.empty(rows, np.float32)
-    r.ref_csr_spmv_seq(C.c_int(rows), C.c_int(cols), _ptr(rp), _ptr(ci), _ptr(v), _ptr(x), _ptr(y))
+    (r.ref_csr_spmv_omp if omp else r.ref_csr_spmv_seq)(C.c_int(rows), C.c_int(cols), _ptr(rp), _ptr(ci), _ptr(v), _ptr(x), _ptr(y))
     return y
 
 

@@ -13,6 +13,7 @@
 #include REF_SEQ_SPGEMM_H
 #include REF_SEQ_SPMV_H
 #include REF_OMP_SPGEMM_H
+#include REF_OMP_SPMV_H
 #include <vector>
 #include <cstdint>
 #include <cstring>
@@ -54,6 +55,15 @@ void ref_csr_spmv_seq(int rows, int cols, const int* rp, const int* ci, const fl
     thrust::cpp::tag exec;
     cusp::system::detail::sequential::multiply(exec, A, X, Y, zero_init(), thrust::multiplies<float>(), thrust::plus<float>(),
                                                cusp::csr_format(), cusp::array1d_format(), cusp::array1d_format());
+}
+
+// y = A x through omp/detail/multiply/csr_spmv.h:43-86 (#pragma omp parallel for over rows)
+void ref_csr_spmv_omp(int rows, int cols, const int* rp, const int* ci, const float* v, const float* x, float* y) {
+    CsrView A{(size_t)rows, (size_t)cols, (size_t)rp[rows], {rp, (size_t)rows + 1}, {ci, (size_t)rp[rows]}, {v, (size_t)rp[rows]}};
+    ViewF X{x, (size_t)cols}; VecOut Y{y};
+    thrust::omp::tag exec;
+    cusp::system::omp::detail::multiply(exec, A, X, Y, zero_init(), thrust::multiplies<float>(), thrust::plus<float>(),
+                                        cusp::csr_format(), cusp::array1d_format(), cusp::array1d_format());
 }
 
 // C = A B; omp == 0: sequential/multiply/csr_spgemm.h:165-197, omp != 0: omp/detail/multiply/csr_spgemm.h:166-198
