@@ -21,8 +21,7 @@
 namespace bmsp {
 
 constexpr int RT = 64;             // block rows per tile (path 0)
-constexpr int SPMV_THREADS = 256;  // 2 matrix rows per thread
-constexpr int STAGES = 4;
+constexpr int SPMV_THREADS = 2 * RT;   // two threads per block row: one per 32-bit bitmap half (4 matrix rows each)
 constexpr int SLICE = 4096;        // blocks per work item (path 1)
 constexpr int ROWSLOT = RT + 4;    // staged row-pointer slice, padded to a 16-byte multiple
 
@@ -36,43 +35,75 @@ struct SpmvArgs {
 };
 
 __host__ __device__ inline size_t stage_bytes(int cap_blk, int cap_val, int vsize) {
-    return (size_t)(cap_blk + 4) * 8 + (size_t)(cap_blk + 4) * 4 + (size_t)(cap_val + 8) * vsize + 2 * ROWSLOT * 4 + 16;
+    return (size_t)(cap_blk + 4) * 8 + (size_t)(cap_blk + 4) * 4 + (size_t)(cap_val + 8) * vsize + 2 * ROWSLOT * 4 + 16 + 16;
 }
 
-template <typename X> __device__ __forceinline__ float ld_x(const X* x, int64_t i);
-template <> __device__ __forceinline__ float ld_x<float>(const float* x, int64_t i) { return __ldg(x + i); }
-template <> __device__ __forceinline__ float ld_x<__half>(const __half* x, int64_t i) { return __half2float(__ldg(x + i)); }
+template <typename X> __device__ __forceinline__ float ld_x(const X* x, uint32_t i);
+template <> __device__ __forceinline__ float ld_x<float>(const float* x, uint32_t i) { return __ldg(x + i); }
+template <> __device__ __forceinline__ float ld_x<__half>(const __half* x, uint32_t i) { return __half2float(__ldg(x + i)); }
 
+// One 8-bit row mask: walk its set bits MSB-first (column 0 first), values are consecutive from kk.
 template <typename T, typename X>
-__global__ void __launch_bounds__(SPMV_THREADS) spmv_rowtile_kernel(SpmvArgs<T> a, const X* __restrict__ x, float* __restrict__ y) {
+__device__ __forceinline__ void row_bits(uint32_t byte, const T* __restrict__ vals, uint32_t& kk, const X* __restrict__ x,
+                                         uint32_t xb7, float& acc) {
+    while (byte) {
+        const uint32_t f = 31u - __clz(byte);          // highest set bit, f = 7 - column
+        acc = fmaf(val_to_f32(vals[kk]), ld_x<X>(x, xb7 - f), acc);
+        kk++;
+        byte ^= 1u << f;
+    }
+}
+
+// The blocks [pb, pe) of one block row, seen by the thread that owns bitmap half `h` (rows 4h..4h+3).
+// bm / bc / vals are indexed relative to the tile's aligned bases (shared memory for staged tiles).
+template <typename T, typename X>
+__device__ __forceinline__ void half_block_row(const uint64_t* __restrict__ bm, const int32_t* __restrict__ bc,
+                                               const T* __restrict__ vals, int pb, int pe, uint32_t k, const int h,
+                                               const X* __restrict__ x, float (&acc)[4]) {
+    for (int b = pb; b < pe; b++) {
+        const uint2 w2 = *reinterpret_cast<const uint2*>(bm + b);     // .y = rows 0-3, .x = rows 4-7
+        const uint32_t nhi = __popc(w2.y), nlo = __popc(w2.x);
+        const uint32_t w = h ? w2.x : w2.y;
+        uint32_t kk = k + (h ? nhi : 0u);
+        k += nhi + nlo;
+        if (w) {
+            const uint32_t xb7 = (uint32_t)bc[b] * 8u + 7u;
+            row_bits<T, X>(w >> 24, vals, kk, x, xb7, acc[0]);
+            row_bits<T, X>((w >> 16) & 0xFFu, vals, kk, x, xb7, acc[1]);
+            row_bits<T, X>((w >> 8) & 0xFFu, vals, kk, x, xb7, acc[2]);
+            row_bits<T, X>(w & 0xFFu, vals, kk, x, xb7, acc[3]);
+        }
+    }
+}
+
+// One CTA per tile, a single staging buffer: latency is hidden by the 16 CTAs (64 warps) resident per SM,
+// each in a different phase (row pointers -> bulk copies in flight -> compute -> store).
+template <typename T, typename X>
+__global__ void __launch_bounds__(SPMV_THREADS, 16) spmv_rowtile_kernel(SpmvArgs<T> a, const X* __restrict__ x, float* __restrict__ y) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int VA = 16 / sizeof(T);   // values per 16 bytes
-    const size_t sb = stage_bytes(a.cap_blk, a.cap_val, sizeof(T));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sb * STAGES);
     const int tid = threadIdx.x;
+    const size_t off_bc = (size_t)(a.cap_blk + 4) * 8, off_val = (size_t)(a.cap_blk + 4) * 12;
+    const size_t off_brp = off_val + (size_t)(a.cap_val + 8) * sizeof(T);
+    uint64_t* s_bm = reinterpret_cast<uint64_t*>(smem);
+    int32_t* s_bc = reinterpret_cast<int32_t*>(smem + off_bc);
+    T* s_val = reinterpret_cast<T*>(smem + off_val);
+    int32_t* s_brp = reinterpret_cast<int32_t*>(smem + off_brp);
+    uint32_t* s_rvb = reinterpret_cast<uint32_t*>(smem + off_brp + ROWSLOT * 4);
+    TileMeta* s_meta = reinterpret_cast<TileMeta*>(smem + off_brp + 2 * ROWSLOT * 4);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + off_brp + 2 * ROWSLOT * 4 + 16);
 
-    auto st_bm   = [&](int s) { return reinterpret_cast<uint64_t*>(smem + sb * s); };
-    auto st_bc   = [&](int s) { return reinterpret_cast<int32_t*>(smem + sb * s + (size_t)(a.cap_blk + 4) * 8); };
-    auto st_val  = [&](int s) { return reinterpret_cast<T*>(smem + sb * s + (size_t)(a.cap_blk + 4) * 12); };
-    auto st_brp  = [&](int s) { return reinterpret_cast<int32_t*>(smem + sb * s + (size_t)(a.cap_blk + 4) * 12 + (size_t)(a.cap_val + 8) * sizeof(T)); };
-    auto st_rvb  = [&](int s) { return reinterpret_cast<uint32_t*>(st_brp(s) + ROWSLOT); };
-    auto st_meta = [&](int s) { return reinterpret_cast<TileMeta*>(st_brp(s) + 2 * ROWSLOT); };
-
+    const int t = blockIdx.x;
+    const int r0 = t * RT, r1 = min(r0 + RT, a.nbr);
     if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
+        mbar_init(bar, 1);
         mbar_fence_init();
-    }
-    __syncthreads();
-
-    // producer (thread 0): stage tile t into ring slot s
-    auto issue = [&](int t, int s) {
-        const int r0 = t * RT, r1 = min(r0 + RT, a.nbr);
         const int p0 = a.brp[r0], p1 = a.brp[r1];
         const uint32_t v0 = a.rvb[r0], v1 = a.rvb[r1];
         TileMeta m;
         m.p0a = p0 & ~1; m.p0c = p0 & ~3; m.v0a = v0 & ~(uint32_t)(VA - 1);
         m.staged = (p1 - p0 <= a.cap_blk) && ((int64_t)v1 - v0 <= a.cap_val);
-        *st_meta(s) = m;
+        *s_meta = m;
         const uint32_t nrow = (uint32_t)(((r1 - r0 + 1) + 3) & ~3) * 4;
         uint32_t n8 = 0, n4 = 0, nv = 0;
         if (m.staged) {
@@ -80,74 +111,27 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_rowtile_kernel(SpmvArgs<T> 
             n4 = (uint32_t)((p1 - m.p0c + 3) & ~3) * 4;
             nv = (uint32_t)((v1 - m.v0a + VA - 1) & ~(uint32_t)(VA - 1)) * sizeof(T);
         }
-        mbar_arrive_expect_tx(&bars[s], n8 + n4 + nv + 2 * nrow);
-        bulk_g2s(st_brp(s), a.brp + r0, nrow, &bars[s]);
-        bulk_g2s(st_rvb(s), a.rvb + r0, nrow, &bars[s]);
-        if (n8) bulk_g2s(st_bm(s), a.bmps + m.p0a, n8, &bars[s]);
-        if (n4) bulk_g2s(st_bc(s), a.bcol + m.p0c, n4, &bars[s]);
-        if (nv) bulk_g2s(st_val(s), a.values + m.v0a, nv, &bars[s]);
-    };
-
-    const int first = blockIdx.x, stride = gridDim.x;
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) {
-            int t = first + s * stride;
-            if (t < a.ntiles) issue(t, s);
-        }
+        mbar_arrive_expect_tx(bar, n8 + n4 + nv + 2 * nrow);
+        bulk_g2s(s_brp, a.brp + r0, nrow, bar);
+        bulk_g2s(s_rvb, a.rvb + r0, nrow, bar);
+        if (n8) bulk_g2s(s_bm, a.bmps + m.p0a, n8, bar);
+        if (n4) bulk_g2s(s_bc, a.bcol + m.p0c, n4, bar);
+        if (nv) bulk_g2s(s_val, a.values + m.v0a, nv, bar);
     }
+    __syncthreads();                 // barrier initialised and armed before anyone polls it
+    mbar_wait(bar, 0);
 
-    // per-thread constants: row inside the 8x8 block
-    const int ri = tid & 7;
-    const int sh = 24 - 8 * (ri & 3);                       // shift of my row byte inside its 32-bit half
-    const uint32_t premask = ~(0xFFFFFFFFu >> (8 * (ri & 3)));   // bits of earlier rows in the same half (0 for ri&3==0)
-    const bool lowhalf = ri >= 4;
-
-    int it = 0;
-    for (int t = first; t < a.ntiles; t += stride, it++) {
-        const int s = it % STAGES;
-        mbar_wait(&bars[s], (uint32_t)((it / STAGES) & 1));
-        const TileMeta m = *st_meta(s);
-        const uint64_t* bm = m.staged ? st_bm(s) : a.bmps + m.p0a;
-        const int32_t* bc = m.staged ? st_bc(s) : a.bcol + m.p0c;
-        const T* vals = m.staged ? st_val(s) : a.values + m.v0a;
-        const int32_t* s_brp = st_brp(s);
-        const uint32_t* s_rvb = st_rvb(s);
-        const int r0 = t * RT;
-#pragma unroll
-        for (int j = 0; j < RT * 8 / SPMV_THREADS; j++) {
-            const int rowi = tid + j * SPMV_THREADS;
-            const int lbr = rowi >> 3;
-            const int64_t row = (int64_t)r0 * 8 + rowi;
-            if (row >= a.rows) continue;
-            const int pb = s_brp[lbr], pe = s_brp[lbr + 1];
-            uint32_t k = s_rvb[lbr] - m.v0a;     // index of the block's first value in `vals`
-            float acc = 0.f;
-            for (int b = pb; b < pe; b++) {
-                const uint64_t bmp = bm[b - m.p0a];
-                const uint32_t hi = (uint32_t)(bmp >> 32), lo = (uint32_t)bmp;
-                const uint32_t w = lowhalf ? lo : hi;
-                uint32_t byte = (w >> sh) & 0xFFu;
-                const uint32_t nhi = __popc(hi);
-                if (byte) {
-                    uint32_t kk = k + __popc(w & premask) + (lowhalf ? nhi : 0u);
-                    const int64_t xb = (int64_t)bc[b - m.p0c] * 8;
-                    do {
-                        const int c = __clz(byte) - 24;          // MSB of the byte is column 0
-                        byte &= ~(0x80u >> c);
-                        acc = fmaf(val_to_f32(vals[kk]), ld_x<X>(x, xb + c), acc);
-                        kk++;
-                    } while (byte);
-                }
-                k += nhi + __popc(lo);
-            }
-            y[row] = acc;
-        }
-        __syncthreads();                      // every thread is done with slot s
-        if (tid == 0) {
-            const int tn = t + STAGES * stride;
-            if (tn < a.ntiles) issue(tn, s);
-        }
-    }
+    const int lbr = tid >> 1, h = tid & 1;
+    const TileMeta m = *s_meta;
+    const int64_t row = ((int64_t)(r0 + lbr)) * 8 + h * 4;
+    if (row >= a.rows) return;
+    const int pb = s_brp[lbr], pe = s_brp[lbr + 1];
+    const uint32_t k = s_rvb[lbr] - m.v0a;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m.staged) half_block_row<T, X>(s_bm - m.p0a, s_bc - m.p0c, s_val, pb, pe, k, h, x, acc);
+    else          half_block_row<T, X>(a.bmps, a.bcol, a.values + m.v0a, pb, pe, k, h, x, acc);
+    if (row + 4 <= a.rows) *reinterpret_cast<float4*>(y + row) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else for (int q = 0; q < 4; q++) if (row + q < a.rows) y[row + q] = acc[q];
 }
 
 // ------------------------------------------------------------------------------------ path 1
@@ -171,7 +155,7 @@ __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __re
         const int b = b0 + lane;
         const bool valid = b < w.z;
         uint64_t bmp = valid ? ld_stream_u64(bmps + b) : 0ull;
-        const int64_t xb = valid ? (int64_t)ld_stream_s32(bcol + b) * 8 : 0;
+        const uint32_t xb = valid ? (uint32_t)ld_stream_s32(bcol + b) * 8u : 0u;
         const uint32_t cnt = __popcll(bmp);
         uint32_t inc = cnt;
 #pragma unroll
@@ -184,7 +168,7 @@ __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __re
         while (bmp) {
             const int p = __clzll((long long)bmp);
             bmp &= ~(0x8000000000000000ull >> p);
-            acc[p >> 3][lane] += val_to_f32(values[k]) * ld_x<X>(x, xb + (p & 7));
+            acc[p >> 3][lane] += val_to_f32(values[k]) * ld_x<X>(x, xb + (uint32_t)(p & 7));
             k++;
         }
     }
@@ -242,9 +226,9 @@ int plan_spmv(bmsp_matrix_s* m, cudaStream_t st) {
     if (m->spmv_path == 0) {
         const int vsize = m->dtype == BMSP_F16 ? 2 : 4;
         double ab = (double)m->nblk / m->nbr * RT, av = (double)m->nnz / m->nbr * RT;
-        int cb = (int)(ab * 1.5) + 64, cv = (int)(av * 1.5) + 256;
+        int cb = (int)(ab * 1.25) + 32, cv = (int)(av * 1.25) + 128;
         cb = (cb + 3) & ~3; cv = (cv + 7) & ~7;
-        const size_t budget = 40 * 1024;
+        const size_t budget = 48 * 1024;
         while (stage_bytes(cb, cv, vsize) > budget && (cb > 64 || cv > 256)) {
             cb = max(64, ((cb * 3 / 4) + 3) & ~3);
             cv = max(256, ((cv * 3 / 4) + 7) & ~7);
@@ -276,20 +260,16 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st) 
         SpmvArgs<T> a;
         a.bmps = A->bmps; a.bcol = A->bcol; a.values = (const T*)A->values; a.brp = A->brp; a.rvb = A->rvb;
         a.rows = A->rows; a.nbr = A->nbr; a.ntiles = (int)ceil_div(A->nbr, RT); a.cap_blk = A->cap_blk; a.cap_val = A->cap_val;
-        const size_t smem = stage_bytes(a.cap_blk, a.cap_val, sizeof(T)) * STAGES + STAGES * 8;
-        static int sms = 0;
+        const size_t smem = stage_bytes(a.cap_blk, a.cap_val, sizeof(T));
         static size_t configured[4] = {0, 0, 0, 0};
         const int inst = (sizeof(T) == 2 ? 0 : 1) * 2 + (sizeof(X) == 2 ? 1 : 0);
         auto kern = spmv_rowtile_kernel<T, X>;
         if (configured[inst] < smem) {
             BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             configured[inst] = smem;
         }
-        if (!sms) { int dev; BMSP_CUDA(cudaGetDevice(&dev)); BMSP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
-        int occ = 0;
-        BMSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SPMV_THREADS, smem));
-        if (occ < 1) { set_error("spmv: kernel does not fit (smem %zu)", smem); return BMSP_ERR_CUDA; }
-        int grid = min(a.ntiles, sms * occ);
+        const int grid = a.ntiles;
         kern<<<grid, SPMV_THREADS, smem, st>>>(a, x, y);
         BMSP_KERNEL_CHECK();
         return BMSP_OK;
