@@ -22,8 +22,9 @@
 
 namespace bmsp {
 
-enum { PASS_COUNT = 0, PASS_FILL = 1, PASS_NUMERIC = 2 };
-enum { MODE_SETBITS = 0, MODE_FILL = 1, MODE_NUMERIC = 2 };
+enum { PASS_COUNT = 0, PASS_FILL = 1, PASS_NUMERIC = 2, PASS_NUMERIC_MMA = 3 };
+enum { MODE_SETBITS = 0, MODE_FILL = 1, MODE_NUMERIC = 2, MODE_MMA = 3 };
+constexpr int QSLOTS = 192;   // per-warp queue: 64 pairs (uint2) + 32 staged PairMeta (32 B each) for the MMA drain
 
 struct GemmArgs {
     const int32_t* a_brp; const int32_t* a_bcol; const uint64_t* a_bmps; const uint8_t* a_kmask; const uint64_t* a_off; const __half* a_val;
@@ -142,6 +143,7 @@ struct RowCtx {
     uint64_t* cbmp;      // FILL: staging (shared or global C.bmps+c0); NUMERIC: shared copy or null
     uint32_t* coff;      // NUMERIC: value offsets relative to the row, or null (global mode)
     float* acc;          // NUMERIC: shared accumulators or null (global atomics)
+    float* dense;        // NUMERIC_MMA: [ccount][64] fp32, lane-private slots (cell (r,c) at (c*4 + r/2) + 32*(r&1))
 };
 
 template <int MODE>
@@ -173,6 +175,80 @@ __device__ __forceinline__ void process_pair(const GemmArgs& g, const RowCtx& r,
                 atomicAdd(dst + rank64(cb, rr * 8 + (q >> 3)), aval * bval);
             }
         }
+    }
+}
+
+// ---- tensor-core path (dense blocks) -----------------------------------------------------------------
+// Two halves of an 8x8 fp16 operand row for mma.m16n8k8: the cells p0 = g*8 + 2t and p0+1 of a block, packed
+// as .f16x2 (absent cells are 0).  Works for the A block (cell = row*8 + k) and for the transposed-operand B
+// block (cell = col*8 + k) alike -- which is exactly why the reference stores B transposed (SPGEMM.cu:309-312).
+__device__ __forceinline__ uint32_t frag_pair(uint64_t bmp, const __half* __restrict__ vals, int p0) {
+    const uint32_t two = (uint32_t)(bmp >> (62 - p0)) & 3u;        // bit1 = cell p0, bit0 = cell p0+1
+    if (!two) return 0u;
+    const int r = rank64(bmp, p0);
+    const unsigned short lo = (two & 2u) ? __half_as_ushort(vals[r]) : (unsigned short)0;
+    const unsigned short hi = (two & 1u) ? __half_as_ushort(vals[r + (int)(two >> 1)]) : (unsigned short)0;
+    return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+
+// Drain n (<= 32) queued (A block, B block) pairs with the whole warp.  Stage 1: lane l fetches the metadata of
+// pair l (bitmaps, value offsets, dense C slot) -- one round of global latency for the whole batch -- into a per-warp
+// shared staging area.  Stage 2: walk the batch; consecutive pairs that share the A block are multiplied two at a
+// time by one mma.sync.m16n8k8 (A-operand = the two B^t blocks stacked, B-operand = the A block, D = the two 8x8
+// fp32 products transposed); the fragments of the next step are loaded before the current MMA is issued.  Each
+// lane owns two fixed slots of every dense C block, so the accumulation needs neither atomics nor warp syncs.
+struct PairMeta { uint64_t abmp, bbmp; uint32_t aoff, boff; int32_t cidx; uint32_t a; };   // 32 bytes
+
+__device__ __forceinline__ void drain_mma(const GemmArgs& g, const RowCtx& r, const uint2* q, int n, PairMeta* sm) {
+    const int lane = threadIdx.x & 31;
+    const int p0 = (lane >> 2) * 8 + (lane & 3) * 2;
+    if (lane < n) {
+        const uint2 e = q[lane];
+        PairMeta m;
+        m.a = e.x;
+        m.abmp = g.a_bmps[e.x]; m.aoff = (uint32_t)g.a_off[e.x];
+        m.bbmp = g.b_bmps[e.y]; m.boff = (uint32_t)g.b_off[e.y];
+        const int j = g.b_bcol[e.y] - r.jbase;
+        m.cidx = (int)r.wrank[j >> 5] + __popc(r.bitset[j >> 5] & ((1u << (j & 31)) - 1u));
+        sm[lane] = m;
+    }
+    __syncwarp();
+    uint32_t fb = 0, fa0 = 0, fa1 = 0, cur_a = 0xFFFFFFFFu;
+    int c0 = 0, c1 = 0;
+    bool two = false;
+    auto load = [&](int i, uint32_t& fb_, uint32_t& fa0_, uint32_t& fa1_, int& c0_, int& c1_, bool& two_, uint32_t& a_) {
+        const PairMeta m0 = sm[i];
+        two_ = (i + 1 < n) && (sm[i + 1].a == m0.a);
+        if (m0.a != a_) { fb_ = frag_pair(m0.abmp, g.a_val + m0.aoff, p0); a_ = m0.a; }
+        fa0_ = frag_pair(m0.bbmp, g.b_val + m0.boff, p0);
+        c0_ = m0.cidx;
+        if (two_) { const PairMeta m1 = sm[i + 1]; fa1_ = frag_pair(m1.bbmp, g.b_val + m1.boff, p0); c1_ = m1.cidx; }
+        else fa1_ = 0u;
+    };
+    int i = 0;
+    if (n > 0) load(0, fb, fa0, fa1, c0, c1, two, cur_a);
+    while (i < n) {
+        const int nxt = i + (two ? 2 : 1);
+        uint32_t nfb = fb, nfa0 = 0, nfa1 = 0, na = cur_a; int nc0 = 0, nc1 = 0; bool ntwo = false;
+        if (nxt < n) load(nxt, nfb, nfa0, nfa1, nc0, nc1, ntwo, na);
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                     : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(fa0), "r"(fa1), "r"(fb));
+        float* a0 = r.dense + c0 * 64 + lane;
+        a0[0] += d0; a0[32] += d1;
+        if (two) { float* a1 = r.dense + c1 * 64 + lane; a1[0] += d2; a1[32] += d3; }
+        i = nxt; fb = nfb; fa0 = nfa0; fa1 = nfa1; c0 = nc0; c1 = nc1; two = ntwo; cur_a = na;
+    }
+    __syncwarp();
+}
+
+template <int MODE>
+__device__ __forceinline__ void drain(const GemmArgs& g, const RowCtx& r, const uint2* q, int n) {
+    if constexpr (MODE == MODE_MMA) {
+        drain_mma(g, r, q, n, reinterpret_cast<PairMeta*>(const_cast<uint2*>(q) + 64));
+    } else {
+        const int lane = threadIdx.x & 31;
+        if (lane < n) { const uint2 e = q[lane]; process_pair<MODE>(g, r, (int)e.x, (int)e.y); }
     }
 }
 
@@ -210,7 +286,8 @@ __device__ __forceinline__ void enumerate_row(const GemmArgs& g, const RowCtx& r
                 qn += __popc(m);
                 __syncwarp();
                 if (qn >= 32) {
-                    const uint2 e = q[lane];
+                    drain<MODE>(g, r, q, 32);
+                    __syncwarp();
                     uint2 t = make_uint2(0, 0);
                     const bool mv = lane + 32 < qn;
                     if (mv) t = q[32 + lane];
@@ -218,13 +295,12 @@ __device__ __forceinline__ void enumerate_row(const GemmArgs& g, const RowCtx& r
                     if (mv) q[lane] = t;
                     qn -= 32;
                     __syncwarp();
-                    process_pair<MODE>(g, r, (int)e.x, (int)e.y);
                 }
             }
         }
     }
     if (MODE != MODE_SETBITS) {
-        if (lane < qn) { const uint2 e = q[lane]; process_pair<MODE>(g, r, (int)e.x, (int)e.y); }
+        drain<MODE>(g, r, q, qn);
         __syncwarp();
     }
 }
@@ -234,17 +310,19 @@ __global__ void __launch_bounds__(256) spgemm_pass_kernel(GemmArgs g) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = T >> 5;
     // shared-memory carve-up (sizes mirrored by pass_smem_bytes on the host)
+    constexpr bool HAS_CBMP = PASS == PASS_FILL || PASS == PASS_NUMERIC;
     uint64_t* s_cbmp = reinterpret_cast<uint64_t*>(smem);                                        // [cap_c]     FILL, NUMERIC
-    uint2* s_queue = reinterpret_cast<uint2*>(s_cbmp + (PASS == PASS_COUNT ? 0 : g.cap_c));       // [nwarps*64] FILL, NUMERIC
-    uint32_t* s_bitset = reinterpret_cast<uint32_t*>(s_queue + (PASS == PASS_COUNT ? 0 : nwarps * 64));   // [cap_words]
-    uint32_t* s_wrank = s_bitset + g.cap_words;                                                   // [cap_words] FILL, NUMERIC
+    uint2* s_queue = reinterpret_cast<uint2*>(s_cbmp + (HAS_CBMP ? g.cap_c : 0));                 // [nwarps*64] all but COUNT
+    uint32_t* s_bitset = reinterpret_cast<uint32_t*>(s_queue + (PASS == PASS_COUNT ? 0 : nwarps * QSLOTS));   // [cap_words]
+    uint32_t* s_wrank = s_bitset + g.cap_words;                                                   // [cap_words] all but COUNT
     uint32_t* s_coff = s_wrank + (PASS == PASS_COUNT ? 0 : g.cap_words);                          // [cap_c]     NUMERIC
     float* s_acc = reinterpret_cast<float*>(s_coff + (PASS == PASS_NUMERIC ? g.cap_c : 0));       // [cap_nnz]   NUMERIC
-    uint32_t* s_tmp = reinterpret_cast<uint32_t*>(s_acc + (PASS == PASS_NUMERIC ? g.cap_nnz : 0)); // [34]
+    float* s_dense = s_acc + (PASS == PASS_NUMERIC ? g.cap_nnz : 0);                              // [cap_c*64]  NUMERIC_MMA
+    uint32_t* s_tmp = reinterpret_cast<uint32_t*>(s_dense + (PASS == PASS_NUMERIC_MMA ? g.cap_c * 64 : 0)); // [34]
     int* s_row = reinterpret_cast<int*>(s_tmp + 34);
 
     unsigned long long n_cand = 0, n_surv = 0;
-    uint2* q = s_queue + wid * 64;
+    uint2* q = s_queue + wid * QSLOTS;
 
     while (true) {
         if (tid == 0) *s_row = g.row_begin + atomicAdd(g.work_counter, 1);
@@ -265,7 +343,7 @@ __global__ void __launch_bounds__(256) spgemm_pass_kernel(GemmArgs g) {
         const bool wfit = nwords <= g.cap_words;
         r.bitset = wfit ? s_bitset : g.g_bitset + (size_t)blockIdx.x * g.max_words;
         r.wrank = wfit ? s_wrank : g.g_wrank + (size_t)blockIdx.x * g.max_words;
-        r.cbmp = nullptr; r.coff = nullptr; r.acc = nullptr; r.c0 = 0;
+        r.cbmp = nullptr; r.coff = nullptr; r.acc = nullptr; r.dense = nullptr; r.c0 = 0;
         for (int w = tid; w < nwords; w += T) r.bitset[w] = 0;
         int ccount = 0;
         if (PASS != PASS_COUNT) { r.c0 = g.c_brp[lrow]; ccount = g.c_brp[lrow + 1] - r.c0; }
@@ -321,6 +399,32 @@ __global__ void __launch_bounds__(256) spgemm_pass_kernel(GemmArgs g) {
             __syncthreads();
             if (fit) for (int v = tid; v < rownnz; v += T) g.c_val[vbase + v] = s_acc[v];
         }
+        if (PASS == PASS_NUMERIC_MMA) {          // launched with one warp per CTA: a block row is owned by one warp
+            const bool fit = ccount <= g.cap_c;
+            if (fit) {
+                r.dense = s_dense;
+                for (int v = tid; v < ccount * 64; v += T) s_dense[v] = 0.f;
+            }
+            for (int c = tid; c < ccount; c += T) {       // bit set from C's own block columns
+                const int j = (int)(g.c_keys[r.c0 + c] & 0xFFFFFFFFull) - r.jbase;
+                atomicOr(&r.bitset[j >> 5], 1u << (j & 31));
+            }
+            __syncthreads();
+            rank_words(r.bitset, r.wrank, nwords, s_tmp);
+            if (fit) enumerate_row<MODE_MMA, false>(g, r, q, n_cand, n_surv);
+            else     enumerate_row<MODE_NUMERIC, false>(g, r, q, n_cand, n_surv);     // global atomics on zeroed C.values
+            __syncthreads();
+            if (fit) {
+                // compact the dense accumulators through C's bitmaps: slot L <-> cell (r = 2t, c = g), slot L+32 <-> (2t+1, g)
+                const int P0 = (lane & 3) * 16 + (lane >> 2);
+                for (int c = wid; c < ccount; c += nwarps) {
+                    const uint64_t bmp = g.c_bmps[r.c0 + c];
+                    float* dst = g.c_val + g.c_off[r.c0 + c];
+                    if ((bmp >> (63 - P0)) & 1ull) dst[rank64(bmp, P0)] = s_dense[c * 64 + lane];
+                    if ((bmp >> (55 - P0)) & 1ull) dst[rank64(bmp, P0 + 8)] = s_dense[c * 64 + 32 + lane];
+                }
+            }
+        }
         __syncthreads();
     }
     if (PASS == PASS_COUNT) {
@@ -332,10 +436,12 @@ __global__ void __launch_bounds__(256) spgemm_pass_kernel(GemmArgs g) {
 
 static size_t pass_smem_bytes(int pass, int T, int cap_words, int cap_c, int cap_nnz) {
     size_t s = 0;
-    if (pass != PASS_COUNT) s += (size_t)cap_c * 8 + (size_t)(T / 32) * 64 * 8;
+    if (pass == PASS_FILL || pass == PASS_NUMERIC) s += (size_t)cap_c * 8;
+    if (pass != PASS_COUNT) s += (size_t)(T / 32) * QSLOTS * 8;
     s += (size_t)cap_words * 4;
     if (pass != PASS_COUNT) s += (size_t)cap_words * 4;
     if (pass == PASS_NUMERIC) s += (size_t)cap_c * 4 + (size_t)cap_nnz * 4;
+    if (pass == PASS_NUMERIC_MMA) s += (size_t)cap_c * 64 * 4;
     s += 34 * 4 + 16;
     return s;
 }
@@ -511,12 +617,23 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     SG_TRY(dev_alloc(&C->values, (size_t)c_nnz * 4 + 16, st));
     if (verbose) SG_CUDA(cudaEventRecord(ev[1], st));
 
-    // ---- NUMERIC
+    // ---- NUMERIC: scalar lanes for sparse blocks, mma.sync for dense ones (about dA*dB/8 products per pair)
     g.c_off = C->offsets; g.c_val = (float*)C->values;
-    g.cap_nnz = std::max(1, std::min(max_rownnz, 12288));
+    const double dA = A->nblk ? (double)A->nnz / A->nblk : 0.0, dB = Bt->nblk ? (double)Bt->nnz / Bt->nblk : 0.0;
+    int path = opts ? opts->numeric_path : -1;
+    if (path < 0) path = (dA * dB / 8.0 >= 40.0) ? 1 : 0;
     if (c_nnz > 0) {
-        if (max_c > g.cap_c || max_rownnz > g.cap_nnz) SG_CUDA(cudaMemsetAsync(C->values, 0, (size_t)c_nnz * 4, st));
-        SG_TRY(launch_pass<PASS_NUMERIC>(g, T, sms, st, nullptr));
+        if (path == 1) {
+            const int cap_keep = g.cap_c;
+            g.cap_c = std::max(1, std::min(max_c, 192));
+            if (max_c > g.cap_c) SG_CUDA(cudaMemsetAsync(C->values, 0, (size_t)c_nnz * 4, st));
+            SG_TRY(launch_pass<PASS_NUMERIC_MMA>(g, 32, sms, st, nullptr));
+            g.cap_c = cap_keep;
+        } else {
+            g.cap_nnz = std::max(1, std::min(max_rownnz, 12288));
+            if (max_c > g.cap_c || max_rownnz > g.cap_nnz) SG_CUDA(cudaMemsetAsync(C->values, 0, (size_t)c_nnz * 4, st));
+            SG_TRY(launch_pass<PASS_NUMERIC>(g, T, sms, st, nullptr));
+        }
     }
     if (verbose) SG_CUDA(cudaEventRecord(ev[2], st));
     SG_TRY(derive_compact(C, st));
@@ -524,7 +641,7 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     if (info) {
         memset(info, 0, sizeof(*info));
         info->candidate_pairs = (int64_t)h_stats[0]; info->surviving_pairs = (int64_t)h_stats[1];
-        info->c_blocks = c_size; info->c_nnz = (int64_t)c_nnz; info->numeric_path = 0;
+        info->c_blocks = c_size; info->c_nnz = (int64_t)c_nnz; info->numeric_path = path;
         if (verbose) {
             SG_CUDA(cudaEventSynchronize(ev[2]));
             cudaEventElapsedTime(&info->symbolic_ms, ev[0], ev[1]);

@@ -68,12 +68,22 @@ def test_fixture_exact(B):
     assert got == exp
 
 
+@pytest.mark.parametrize("path", [0, 1])
 @pytest.mark.parametrize("n,m,p,density", [(24, 24, 24, 0.2), (61, 45, 29, 0.15), (300, 200, 250, 0.05), (257, 513, 129, 0.3),
                                            (1000, 1000, 1000, 0.004), (64, 64, 64, 0.9)])
-def test_random(B, oracle, n, m, p, density):
+def test_random(B, oracle, n, m, p, density, path):
+    """path 0 = scalar lanes, path 1 = mma.sync m16n8k8 (forced on every density, also the sparse ones)"""
     a = random_csr(n, m, density, seed=n * 7 + m, empty_block_rows=(1,) if n > 24 else ())
     b = random_csr(m, p, density, seed=m * 13 + p, empty_block_rows=(0, 3) if m > 40 else ())
-    _mult_check(B, oracle, (n, m), a, (m, p), b)
+    C, info, exp = _mult_check(B, oracle, (n, m), a, (m, p), b, numeric_path=path)
+    assert info.numeric_path == path
+
+
+def test_mma_path_wide_rows_fall_back(B, oracle):
+    """a block row of C with more blocks than the dense-accumulator cap (192) must take the global fallback"""
+    a = random_csr(16, 64, 0.9, seed=3)
+    b = random_csr(64, 8 * 400, 0.5, seed=4)
+    _mult_check(B, oracle, (16, 64), a, (64, 8 * 400), b, numeric_path=1)
 
 
 def test_generators_square(B, oracle):
@@ -83,6 +93,7 @@ def test_generators_square(B, oracle):
         nr, nc, rp, ci, v = gen()
         C, info, exp = _mult_check(B, oracle, (nr, nc), (rp, ci, v), (nr, nc), (rp, ci, v))
         assert info.surviving_pairs <= info.candidate_pairs
+        _mult_check(B, oracle, (nr, nc), (rp, ci, v), (nr, nc), (rp, ci, v), numeric_path=1 - info.numeric_path)
 
 
 def test_poisson256_counts(B):
