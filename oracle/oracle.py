@@ -243,3 +243,59 @@ def read_mtx(path):
             if sym and i != j:
                 r.append(j); c.append(i); v.append(x)
     return nr, nc, np.array(r, np.int32), np.array(c, np.int32), np.array(v, np.float64)
+
+
+# ------------------------------------------------------------------ the reference's own CUDA operators (GPU box only)
+def ref_cuda_bin(name: str):
+    """oracle/_ref/ref_spgemm | ref_spmv: the reference's bmSparse_mult / bmSparse_SpMV compiled for sm_100 from
+    /root/reference by `make -C oracle refcuda`; None when they were never built."""
+    p = os.path.join(_HERE, "_ref", name)
+    return p if os.path.exists(p) else None
+
+
+def write_bin(path, m: OracleMatrix, value_dtype):
+    v = np.ascontiguousarray(m.values, dtype=value_dtype)
+    with open(path, "wb") as f:
+        np.array([m.num_rows, m.num_cols, m.block_num, v.size, v.itemsize], np.int64).tofile(f)
+        np.ascontiguousarray(m.keys, np.uint64).tofile(f)
+        np.ascontiguousarray(m.bmps, np.uint64).tofile(f)
+        np.ascontiguousarray(m.offsets[:m.block_num], np.uint64).tofile(f)
+        v.tofile(f)
+
+
+def run_ref_spgemm(a: OracleMatrix, bt: OracleMatrix, workdir, tc_version=5, mode=0, reps=1, keep=True):
+    """Run the reference's bmSparse_mult<half,float> on the GPU.  Returns (C as OracleMatrix fp32, best microseconds)."""
+    exe = ref_cuda_bin("ref_spgemm")
+    pa, pb, pc = (os.path.join(workdir, n) for n in ("refA.bin", "refB.bin", "refC.bin"))
+    write_bin(pa, a, np.float16); write_bin(pb, bt, np.float16)
+    out = subprocess.run([exe, pa, pb, pc, str(tc_version), str(mode), str(reps)], capture_output=True, text=True, timeout=1800)
+    line = [l for l in out.stdout.splitlines() if l.startswith("REF_SPGEMM_US")]
+    if out.returncode != 0 or not line:
+        raise RuntimeError(f"reference spgemm failed: rc={out.returncode}\n{out.stdout[-2000:]}\n{out.stderr[-2000:]}")
+    tok = line[0].split()
+    us, status = float(tok[1]), int(tok[7])
+    if status != 0:
+        raise RuntimeError(f"reference spgemm left CUDA error {status}")
+    with open(pc, "rb") as f:
+        h = np.fromfile(f, np.int64, 5)
+        k = np.fromfile(f, np.uint64, h[2]); b = np.fromfile(f, np.uint64, h[2]); o = np.fromfile(f, np.uint64, h[4])
+        v = np.fromfile(f, np.float32, h[3])
+    if not keep:
+        for p in (pa, pb, pc):
+            os.remove(p)
+    return OracleMatrix(int(h[0]), int(h[1]), k, b, o, v, False), us
+
+
+def run_ref_spmv(a: OracleMatrix, workdir, reps=1):
+    """Run the reference's bmSparse_SpMV<float,float> (x = ones, as its main does).  Returns (y, best microseconds)."""
+    exe = ref_cuda_bin("ref_spmv")
+    pa, py = os.path.join(workdir, "refA32.bin"), os.path.join(workdir, "refY.bin")
+    write_bin(pa, a, np.float32)
+    out = subprocess.run([exe, pa, py, str(reps)], capture_output=True, text=True, timeout=1800)
+    line = [l for l in out.stdout.splitlines() if l.startswith("REF_SPMV_US")]
+    if out.returncode != 0 or not line:
+        raise RuntimeError(f"reference spmv failed: rc={out.returncode}\n{out.stdout[-2000:]}\n{out.stderr[-2000:]}")
+    us = float(line[0].split()[1])
+    with open(py, "rb") as f:
+        n = int(np.fromfile(f, np.int64, 1)[0]); y = np.fromfile(f, np.float32, n)
+    return y, us

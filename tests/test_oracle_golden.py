@@ -132,3 +132,27 @@ def test_generators_shapes():
     for r in range(0, n, 41):
         assert np.all(np.diff(ci[rp[r]:rp[r + 1]]) > 0)
     assert np.all(v.astype(np.float16).astype(np.float32) == v)
+
+
+def test_oracle_matches_recorded_reference_cuda_outputs(oracle):
+    """tests/golden/ref_cuda_golden.json was written on the B200 box by tests/test_gpu_reference_cuda.py from the
+    reference's OWN bmSparse_mult / bmSparse_SpMV (compiled for sm_100 into oracle/_ref).  The oracle must reproduce
+    the recorded structure fingerprints exactly and the value sums within the reference's fp16-product rounding."""
+    from tests.util import random_csr
+    O = oracle
+    rec = load_golden("ref_cuda_golden.json")["cases"]
+    g = load_golden("ragusa16.json")
+    mats = {"ragusa16_AxB": (O.coo_to_bmsp(24, 24, g["A"]["rows"], g["A"]["cols"], g["A"]["vals"]),
+                             O.coo_to_bmsp(24, 24, g["B"]["rows"], g["B"]["cols"], g["B"]["vals"], transposed=True))}
+    rp, ci, v = O.poisson5pt(64, 64)
+    mats["poisson64_AxA"] = (O.csr_to_bmsp(4096, 4096, rp, ci, v), O.csr_to_bmsp(4096, 4096, rp, ci, v, transposed=True))
+    a32 = O.csr_to_bmsp(4096, 4096, rp, ci, v, f16=False)
+    rp, ci, v = random_csr(256, 256, 0.06, seed=77)
+    mats["random256_AxA"] = (O.csr_to_bmsp(256, 256, rp, ci, v), O.csr_to_bmsp(256, 256, rp, ci, v, transposed=True))
+    for name, (a, bt) in mats.items():
+        exp = O.spgemm(a, bt); r = rec[name]
+        assert exp.block_num == r["C_blocks"] and exp.nnz == r["C_nnz"] == r["offsets_last"], name
+        assert int(np.bitwise_xor.reduce(exp.keys)) == r["keys_crc"] and int(np.bitwise_xor.reduce(exp.bmps)) == r["bmps_crc"], name
+        assert abs(float(exp.values.sum()) - r["values_sum"]) <= 2e-3 * float(np.abs(exp.values).sum()) + 1e-6, name
+    y = O.spmv(a32, np.ones(4096, np.float32))
+    assert float(y.sum()) == rec["poisson64_spmv_ones"]["y_sum"] and float(np.abs(y).sum()) == rec["poisson64_spmv_ones"]["y_abs_sum"]
