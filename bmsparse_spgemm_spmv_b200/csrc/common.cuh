@@ -27,7 +27,7 @@ struct bmsp_matrix_s {
     uint32_t* rvb = nullptr;    // [nbr+1] first value index of each block row
     uint8_t* kmask = nullptr;   // [nblk]  OR of the 8 bitmap bytes: inner-dimension (k) occupancy
     // SpMV plan (spmv.cu)
-    int32_t spmv_path = -1;     // 0 row-tiled (dense-ish blocks), 1 block-parallel (sparse blocks)
+    int32_t spmv_path = -2;     // -2 not planned yet, 0 row-tiled (dense-ish blocks), 1 block-parallel (sparse blocks)
     int32_t cap_blk = 0, cap_val = 0;   // per-stage smem capacities of the row-tiled kernel
     int32_t* work = nullptr;    // block-parallel work items (int4 per item)
     int32_t n_work = 0, n_split = 0;

@@ -185,7 +185,8 @@ int derive_compact(bmsp_matrix_s* m, cudaStream_t st) {
     derive_rows_kernel<<<(unsigned)ceil_div(m->nbr + 1, 256), 256, 0, st>>>(m->keys, m->offsets, m->brp, m->rvb, m->nblk,
                                                                           m->nbr, (uint64_t)m->nnz);
     BMSP_KERNEL_CHECK();
-    return plan_spmv(m, st);
+    m->spmv_path = -2;      // SpMV plan is built lazily by the first bmsp_spmv
+    return BMSP_OK;
 }
 
 }  // namespace bmsp

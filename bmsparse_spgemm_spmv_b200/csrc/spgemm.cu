@@ -6,14 +6,17 @@
 // the task list before its numeric kernel.  Here nothing is materialised and nothing is sorted:
 //
 //   row-wise (Gustavson) over A's block rows, one CTA per block row (dynamic queue), three passes
-//     COUNT   survivors of the 1-byte inner-dimension test (kmask_a & kmask_b) set a bit in a per-row
-//             bit set over C's block columns            -> C blocks per block row  (T_1..T_4)
-//     FILL    same bit set, ranked by a popc prefix: the rank of column j IS its sorted position, so
-//             C.keys come out ascending without a sort (replaces T_5/T_6 and bb_segsort); the
-//             boolean 8x8 product of the operand bitmaps is OR-ed into the block's bitmap   (T_9)
-//     NUMERIC bit set rebuilt from C.keys; every surviving pair is multiplied (scalar path for sparse
-//             blocks, mma.sync m16n8k8 fp16->fp32 path for dense blocks, two B blocks per MMA) and
-//             accumulated in shared memory, then stored coalesced                           (T_7)
+//     COUNT   candidates are tested four at a time (one 32-bit load of B's inner-dimension masks against the
+//             replicated mask of the A block); survivors set a bit in a per-row bit set over C's block
+//             columns                                   -> C blocks and survivors per block row  (T_1..T_4)
+//     FILL    same walk; survivors are also appended to a global pair list (8 B each -- the only thing that
+//             is materialised, after the filter, never sorted).  The bit set is ranked by a popc prefix: the
+//             rank of column j IS its sorted position, so C.keys come out ascending without a sort
+//             (replaces T_5/T_6 and bb_segsort); the boolean 8x8 product of the operand bitmaps is OR-ed
+//             into the block's bitmap; value offsets are scanned per row                              (T_9)
+//     NUMERIC bit set rebuilt from C.keys; the pair list is multiplied (scalar lanes for sparse blocks,
+//             mma.sync m16n8k8 fp16->fp32 for dense blocks, two B blocks per MMA) and accumulated in
+//             shared memory, then stored coalesced                                                    (T_7)
 //   block rows whose bit set / block list / value list exceed the shared-memory caps run the same
 //   code on global scratch.
 #include "common.cuh"
@@ -36,10 +39,14 @@ struct GemmArgs {
     uint32_t* g_bitset; uint32_t* g_wrank; int32_t max_words;   // per-CTA global scratch for over-cap rows
     int32_t* work_counter;
     uint32_t* row_count;       // COUNT out: C blocks per row (indexed row - row_begin)
+    uint32_t* row_surv;        // COUNT out: surviving pairs per row; FILL/NUMERIC in: exclusive scan of it
+    uint2* surv_list;          // FILL out / NUMERIC in: (A block, B block) of every surviving pair, row-segmented
     int32_t* maxes;            // [0] max words, [1] max C blocks per row, [2] max C values per row
     const int32_t* c_brp;      // FILL/NUMERIC in: C block-row pointers (indexed row - row_begin)
-    uint64_t* c_keys; uint64_t* c_bmps;
-    const uint64_t* c_off; float* c_val;
+    uint64_t* c_keys; uint64_t* c_bmps; int32_t* c_bcol; uint8_t* c_kmask;
+    uint64_t* c_off;           // FILL out: value offsets relative to the row; NUMERIC: rebased to absolute
+    uint64_t* row_nnz;         // FILL out: values per row; NUMERIC in: exclusive scan of it (row value base)
+    float* c_val;
     unsigned long long* stats; // [0] candidate pairs, [1] surviving pairs (COUNT pass)
 };
 
@@ -153,7 +160,10 @@ __device__ __forceinline__ void process_pair(const GemmArgs& g, const RowCtx& r,
     const uint32_t word = r.bitset[j >> 5];
     const int c = (int)r.wrank[j >> 5] + __popc(word & ((1u << (j & 31)) - 1u));
     if (MODE == MODE_FILL) {
-        atomicOr((unsigned long long*)&r.cbmp[c], (unsigned long long)pair_bitmap(abmp, bbmp));
+        const uint64_t pb = pair_bitmap(abmp, bbmp);
+        unsigned int* w = reinterpret_cast<unsigned int*>(&r.cbmp[c]);      // native 32-bit ATOMS.OR, not a 64-bit CAS loop
+        if ((uint32_t)pb) atomicOr(w, (unsigned int)pb);
+        if ((uint32_t)(pb >> 32)) atomicOr(w + 1, (unsigned int)(pb >> 32));
     } else {
         const __half* av = g.a_val + g.a_off[a];
         const __half* bv = g.b_val + g.b_off[b];
@@ -252,6 +262,106 @@ __device__ __forceinline__ void drain(const GemmArgs& g, const RowCtx& r, const 
     }
 }
 
+// Candidate walk, four B blocks per lane and step: `slots` A blocks at a time, G lanes per A block, each lane
+// tests one aligned 32-bit word of B's inner-dimension masks (kmask) against the replicated mask of its A block.
+// Survivors set their C block column in the row's bit set; with LIST they are also appended to the row's segment
+// of the global pair list (one shared cursor bump per warp and step).
+template <bool LIST, bool STATS>
+__device__ __forceinline__ void enumerate_vec(const GemmArgs& g, const RowCtx& r, uint2* list, uint32_t* s_cursor,
+                                              unsigned long long& n_cand, uint32_t& n_surv) {
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+    const int Gs = g.G, slots = T / Gs, slot = tid / Gs, gl = tid % Gs;
+    const int niter = (r.a1 - r.a0 + slots - 1) / slots;
+    for (int itA = 0; itA < niter; itA++) {
+        const int a = r.a0 + itA * slots + slot;
+        int b0 = 0, b1 = 0; uint32_t am4 = 0;
+        if (a < r.a1) {
+            const int k = g.a_bcol[a];
+            b0 = g.b_brp[k]; b1 = g.b_brp[k + 1];
+            am4 = (uint32_t)g.a_kmask[a] * 0x01010101u;
+        }
+        const int bs = b0 & ~3;
+        int ngrp = (b1 - bs + 3) >> 2;           // 4-block groups of this lane's B row (0 when the row is empty)
+        if (b1 <= b0) ngrp = 0;
+        int maxgrp = ngrp;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) maxgrp = max(maxgrp, __shfl_xor_sync(0xffffffffu, maxgrp, o));
+        for (int grp0 = 0; grp0 < maxgrp; grp0 += Gs) {
+            const int grp = grp0 + gl;
+            const int bb = bs + 4 * grp;
+            uint32_t nz = 0;
+            if (grp < ngrp) {
+                const uint32_t km4 = *reinterpret_cast<const uint32_t*>(g.b_kmask + bb);
+                const int lo = max(b0 - bb, 0), hi = min(b1 - bb, 4);          // valid bytes [lo, hi)
+                const uint32_t vm = (0xFFFFFFFFu << (8 * lo)) & (hi >= 4 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu << (8 * hi)));
+                nz = __vcmpne4(km4 & am4, 0u) & vm;                              // 0xFF in every surviving byte
+                if (STATS) { n_cand += (unsigned)(hi - lo); }
+            }
+            const int cnt = __popc(nz) >> 3;
+            if (STATS) n_surv += cnt;
+            uint32_t rem = nz;
+            if (LIST) {
+                // recompute per-byte positions without packing tricks (at most 4 survivors per lane)
+                uint32_t total = 0, base = 0;
+                uint32_t p4[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const bool s = (nz >> (8 * i)) & 1u;
+                    const uint32_t m = __ballot_sync(0xffffffffu, s);
+                    p4[i] = total + __popc(m & ((1u << lane) - 1u));
+                    total += __popc(m);
+                }
+                if (total) {
+                    if (lane == 0) base = atomicAdd(s_cursor, total);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if ((nz >> (8 * i)) & 1u) list[base + p4[i]] = make_uint2((uint32_t)a, (uint32_t)(bb + i));
+                }
+            }
+            while (rem) {
+                const int i = (__ffs(rem) - 1) >> 3;
+                rem &= ~(0xFFu << (8 * i));
+                const int j = g.b_bcol[bb + i] - r.jbase;
+                atomicOr(&r.bitset[j >> 5], 1u << (j & 31));
+            }
+        }
+    }
+}
+
+// CTA-wide exclusive scan of popc(bmp[c]), c < n: writes the 64-bit prefix to off[c] and returns the total.
+__device__ __forceinline__ uint32_t scan_popc64(const uint64_t* bmp, uint64_t* off, int n, uint32_t* s_tmp) {
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (n + T - 1) / T;
+    const int c0 = min(tid * per, n), c1 = min(c0 + per, n);
+    uint32_t s = 0;
+    for (int c = c0; c < c1; c++) s += __popcll(bmp[c]);
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_tmp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = lane < (T >> 5) ? s_tmp[lane] : 0, vi = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
+            if (lane >= o) vi += t;
+        }
+        s_tmp[lane] = vi - v;
+        if (lane == 31) s_tmp[32] = vi;
+    }
+    __syncthreads();
+    uint32_t run = s_tmp[wid] + inc - s;
+    for (int c = c0; c < c1; c++) { off[c] = run; run += __popcll(bmp[c]); }
+    const uint32_t total = s_tmp[32];
+    __syncthreads();
+    return total;
+}
+
 // Walk the row's candidate pairs: `slots` A blocks at a time, G lanes per A block striding over the
 // B block row.  MODE_SETBITS marks C block columns; the other modes compact survivors through a
 // per-warp queue so that all 32 lanes work on surviving pairs.
@@ -311,21 +421,23 @@ __global__ void __launch_bounds__(256) spgemm_pass_kernel(GemmArgs g) {
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = T >> 5;
     // shared-memory carve-up (sizes mirrored by pass_smem_bytes on the host)
     constexpr bool HAS_CBMP = PASS == PASS_FILL || PASS == PASS_NUMERIC;
+    constexpr bool HAS_QUEUE = PASS == PASS_NUMERIC_MMA;
     uint64_t* s_cbmp = reinterpret_cast<uint64_t*>(smem);                                        // [cap_c]     FILL, NUMERIC
-    uint2* s_queue = reinterpret_cast<uint2*>(s_cbmp + (HAS_CBMP ? g.cap_c : 0));                 // [nwarps*64] all but COUNT
-    uint32_t* s_bitset = reinterpret_cast<uint32_t*>(s_queue + (PASS == PASS_COUNT ? 0 : nwarps * QSLOTS));   // [cap_words]
+    uint2* s_queue = reinterpret_cast<uint2*>(s_cbmp + (HAS_CBMP ? g.cap_c : 0));                 // [nwarps*QSLOTS] NUMERIC_MMA
+    uint32_t* s_bitset = reinterpret_cast<uint32_t*>(s_queue + (HAS_QUEUE ? nwarps * QSLOTS : 0)); // [cap_words]
     uint32_t* s_wrank = s_bitset + g.cap_words;                                                   // [cap_words] all but COUNT
     uint32_t* s_coff = s_wrank + (PASS == PASS_COUNT ? 0 : g.cap_words);                          // [cap_c]     NUMERIC
     float* s_acc = reinterpret_cast<float*>(s_coff + (PASS == PASS_NUMERIC ? g.cap_c : 0));       // [cap_nnz]   NUMERIC
     float* s_dense = s_acc + (PASS == PASS_NUMERIC ? g.cap_nnz : 0);                              // [cap_c*64]  NUMERIC_MMA
     uint32_t* s_tmp = reinterpret_cast<uint32_t*>(s_dense + (PASS == PASS_NUMERIC_MMA ? g.cap_c * 64 : 0)); // [34]
     int* s_row = reinterpret_cast<int*>(s_tmp + 34);
+    uint32_t* s_cursor = reinterpret_cast<uint32_t*>(s_row + 1);
 
-    unsigned long long n_cand = 0, n_surv = 0;
+    unsigned long long n_cand = 0, n_surv_total = 0;
     uint2* q = s_queue + wid * QSLOTS;
 
     while (true) {
-        if (tid == 0) *s_row = g.row_begin + atomicAdd(g.work_counter, 1);
+        if (tid == 0) { *s_row = g.row_begin + atomicAdd(g.work_counter, 1); *s_cursor = 0; }
         __syncthreads();
         RowCtx r;
         r.row = *s_row;
@@ -337,7 +449,8 @@ __global__ void __launch_bounds__(256) spgemm_pass_kernel(GemmArgs g) {
         const int nwords = ri.y;
         r.a0 = g.a_brp[r.row]; r.a1 = g.a_brp[r.row + 1];
         if (nwords == 0) {
-            if (PASS == PASS_COUNT && tid == 0) g.row_count[lrow] = 0;
+            if (PASS == PASS_COUNT && tid == 0) { g.row_count[lrow] = 0; g.row_surv[lrow] = 0; }
+            if (PASS == PASS_FILL && tid == 0) g.row_nnz[lrow] = 0;
             continue;
         }
         const bool wfit = nwords <= g.cap_words;
@@ -346,75 +459,92 @@ __global__ void __launch_bounds__(256) spgemm_pass_kernel(GemmArgs g) {
         r.cbmp = nullptr; r.coff = nullptr; r.acc = nullptr; r.dense = nullptr; r.c0 = 0;
         for (int w = tid; w < nwords; w += T) r.bitset[w] = 0;
         int ccount = 0;
-        if (PASS != PASS_COUNT) { r.c0 = g.c_brp[lrow]; ccount = g.c_brp[lrow + 1] - r.c0; }
-        if (PASS != PASS_COUNT && ccount == 0) { __syncthreads(); continue; }
+        uint32_t s0 = 0, nsurv = 0;
+        if (PASS != PASS_COUNT) {
+            r.c0 = g.c_brp[lrow]; ccount = g.c_brp[lrow + 1] - r.c0;
+            s0 = g.row_surv[lrow]; nsurv = g.row_surv[lrow + 1] - s0;
+        }
+        if (PASS != PASS_COUNT && ccount == 0) {
+            if (PASS == PASS_FILL && tid == 0) g.row_nnz[lrow] = 0;
+            __syncthreads();
+            continue;
+        }
+        uint2* list = g.surv_list + s0;
 
         if (PASS == PASS_COUNT) {
             __syncthreads();
-            enumerate_row<MODE_SETBITS, true>(g, r, q, n_cand, n_surv);
+            uint32_t ns = 0;
+            enumerate_vec<false, true>(g, r, nullptr, nullptr, n_cand, ns);
+            n_surv_total += ns;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+            if (lane == 0 && ns) atomicAdd(s_cursor, ns);
             __syncthreads();
             const uint32_t total = rank_words(r.bitset, nullptr, nwords, s_tmp);
-            if (tid == 0) { g.row_count[lrow] = total; atomicMax(g.maxes + 1, (int)total); }
+            if (tid == 0) { g.row_count[lrow] = total; g.row_surv[lrow] = *s_cursor; atomicMax(g.maxes + 1, (int)total); }
         }
         if (PASS == PASS_FILL) {
             const bool cfit = ccount <= g.cap_c;
             r.cbmp = cfit ? s_cbmp : g.c_bmps + r.c0;          // global C.bmps is pre-zeroed
             if (cfit) for (int c = tid; c < ccount; c += T) r.cbmp[c] = 0;
             __syncthreads();
-            enumerate_row<MODE_SETBITS, false>(g, r, q, n_cand, n_surv);
+            uint32_t ns = 0;
+            enumerate_vec<true, false>(g, r, list, s_cursor, n_cand, ns);     // bits + pair list
             __syncthreads();
             rank_words(r.bitset, r.wrank, nwords, s_tmp);
-            enumerate_row<MODE_FILL, false>(g, r, q, n_cand, n_surv);
+            for (uint32_t e = tid; e < nsurv; e += T) { const uint2 pr = list[e]; process_pair<MODE_FILL>(g, r, (int)pr.x, (int)pr.y); }
             __syncthreads();
-            // keys + bitmaps out: ascending bit index = ascending block column
+            // keys, bitmaps and the derived per-block arrays out: ascending bit index = ascending block column
             for (int w = tid; w < nwords; w += T) {
                 uint32_t word = r.bitset[w];
                 int c = (int)r.wrank[w];
                 while (word) {
                     const int bit = __ffs(word) - 1;
                     word &= word - 1;
-                    g.c_keys[r.c0 + c] = ((uint64_t)(uint32_t)r.row << 32) | (uint32_t)(r.jbase + w * 32 + bit);
-                    if (cfit) g.c_bmps[r.c0 + c] = r.cbmp[c];
+                    const int j = r.jbase + w * 32 + bit;
+                    const uint64_t bm = r.cbmp[c];
+                    g.c_keys[r.c0 + c] = ((uint64_t)(uint32_t)r.row << 32) | (uint32_t)j;
+                    g.c_bcol[r.c0 + c] = j;
+                    g.c_kmask[r.c0 + c] = (uint8_t)kmask_of(bm);
+                    if (cfit) g.c_bmps[r.c0 + c] = bm;
                     c++;
                 }
             }
-        }
-        if (PASS == PASS_NUMERIC) {
-            const uint64_t vbase = g.c_off[r.c0];
-            const int64_t rownnz = (int64_t)(g.c_off[r.c0 + ccount] - vbase);
-            const bool fit = ccount <= g.cap_c && rownnz <= g.cap_nnz;
-            if (fit) {
-                r.cbmp = s_cbmp; r.coff = s_coff; r.acc = s_acc;
-                for (int c = tid; c < ccount; c += T) { s_cbmp[c] = g.c_bmps[r.c0 + c]; s_coff[c] = (uint32_t)(g.c_off[r.c0 + c] - vbase); }
-                for (int v = tid; v < rownnz; v += T) s_acc[v] = 0.f;
-            }
             __syncthreads();
-            for (int c = tid; c < ccount; c += T) {       // bit set from C's own block columns
-                const int j = (int)(g.c_keys[r.c0 + c] & 0xFFFFFFFFull) - r.jbase;
+            // value offsets relative to the row (NUMERIC rebases them once the row totals are scanned)
+            const uint32_t rn = scan_popc64(r.cbmp, g.c_off + r.c0, ccount, s_tmp);
+            if (tid == 0) { g.row_nnz[lrow] = rn; atomicMax(g.maxes + 2, (int)min(rn, 0x7FFFFFFFu)); }
+        }
+        if (PASS == PASS_NUMERIC || PASS == PASS_NUMERIC_MMA) {
+            const uint64_t vbase = g.row_nnz[lrow];
+            const int64_t rownnz = (int64_t)(g.row_nnz[lrow + 1] - vbase);
+            const bool fit = PASS == PASS_NUMERIC ? (ccount <= g.cap_c && rownnz <= g.cap_nnz) : (ccount <= g.cap_c);
+            for (int c = tid; c < ccount; c += T) {
+                const uint64_t local = g.c_off[r.c0 + c];
+                if (PASS == PASS_NUMERIC && fit) { s_cbmp[c] = g.c_bmps[r.c0 + c]; s_coff[c] = (uint32_t)local; }
+                g.c_off[r.c0 + c] = vbase + local;                           // absolute from here on
+                const int j = g.c_bcol[r.c0 + c] - r.jbase;                 // bit set from C's own block columns
                 atomicOr(&r.bitset[j >> 5], 1u << (j & 31));
             }
-            __syncthreads();
-            rank_words(r.bitset, r.wrank, nwords, s_tmp);
-            enumerate_row<MODE_NUMERIC, false>(g, r, q, n_cand, n_surv);
-            __syncthreads();
-            if (fit) for (int v = tid; v < rownnz; v += T) g.c_val[vbase + v] = s_acc[v];
-        }
-        if (PASS == PASS_NUMERIC_MMA) {          // launched with one warp per CTA: a block row is owned by one warp
-            const bool fit = ccount <= g.cap_c;
-            if (fit) {
+            if (PASS == PASS_NUMERIC && fit) {
+                r.cbmp = s_cbmp; r.coff = s_coff; r.acc = s_acc;
+                for (int v = tid; v < rownnz; v += T) s_acc[v] = 0.f;
+            }
+            if (PASS == PASS_NUMERIC_MMA && fit) {
                 r.dense = s_dense;
                 for (int v = tid; v < ccount * 64; v += T) s_dense[v] = 0.f;
             }
-            for (int c = tid; c < ccount; c += T) {       // bit set from C's own block columns
-                const int j = (int)(g.c_keys[r.c0 + c] & 0xFFFFFFFFull) - r.jbase;
-                atomicOr(&r.bitset[j >> 5], 1u << (j & 31));
-            }
             __syncthreads();
             rank_words(r.bitset, r.wrank, nwords, s_tmp);
-            if (fit) enumerate_row<MODE_MMA, false>(g, r, q, n_cand, n_surv);
-            else     enumerate_row<MODE_NUMERIC, false>(g, r, q, n_cand, n_surv);     // global atomics on zeroed C.values
+            if (PASS == PASS_NUMERIC || !fit) {
+                for (uint32_t e = tid; e < nsurv; e += T) { const uint2 pr = list[e]; process_pair<MODE_NUMERIC>(g, r, (int)pr.x, (int)pr.y); }
+            } else {
+                unsigned long long dc = 0, ds = 0;
+                enumerate_row<MODE_MMA, false>(g, r, q, dc, ds);          // one warp per block row: pairs of an A block stay adjacent
+            }
             __syncthreads();
-            if (fit) {
+            if (PASS == PASS_NUMERIC && fit) for (int v = tid; v < rownnz; v += T) g.c_val[vbase + v] = s_acc[v];
+            if (PASS == PASS_NUMERIC_MMA && fit) {
                 // compact the dense accumulators through C's bitmaps: slot L <-> cell (r = 2t, c = g), slot L+32 <-> (2t+1, g)
                 const int P0 = (lane & 3) * 16 + (lane >> 2);
                 for (int c = wid; c < ccount; c += nwarps) {
@@ -429,32 +559,34 @@ __global__ void __launch_bounds__(256) spgemm_pass_kernel(GemmArgs g) {
     }
     if (PASS == PASS_COUNT) {
 #pragma unroll
-        for (int o = 16; o; o >>= 1) { n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o); n_surv += __shfl_xor_sync(0xffffffffu, n_surv, o); }
-        if (lane == 0) { atomicAdd(g.stats, n_cand); atomicAdd(g.stats + 1, n_surv); }
+        for (int o = 16; o; o >>= 1) { n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o); n_surv_total += __shfl_xor_sync(0xffffffffu, n_surv_total, o); }
+        if (lane == 0) { atomicAdd(g.stats, n_cand); atomicAdd(g.stats + 1, n_surv_total); }
     }
 }
 
 static size_t pass_smem_bytes(int pass, int T, int cap_words, int cap_c, int cap_nnz) {
     size_t s = 0;
     if (pass == PASS_FILL || pass == PASS_NUMERIC) s += (size_t)cap_c * 8;
-    if (pass != PASS_COUNT) s += (size_t)(T / 32) * QSLOTS * 8;
+    if (pass == PASS_NUMERIC_MMA) s += (size_t)(T / 32) * QSLOTS * 8;
     s += (size_t)cap_words * 4;
     if (pass != PASS_COUNT) s += (size_t)cap_words * 4;
     if (pass == PASS_NUMERIC) s += (size_t)cap_c * 4 + (size_t)cap_nnz * 4;
     if (pass == PASS_NUMERIC_MMA) s += (size_t)cap_c * 64 * 4;
-    s += 34 * 4 + 16;
+    s += 36 * 4 + 16;
     return s;
 }
 
-__global__ void popc_kernel(const uint64_t* __restrict__ bmps, uint64_t* __restrict__ out, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (uint64_t)__popcll(bmps[i]);
-}
-__global__ void row_nnz_max_kernel(const int32_t* __restrict__ c_brp, const uint64_t* __restrict__ c_off, int nrows, int* __restrict__ maxes) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nrows) return;
-    uint64_t n = c_off[c_brp[i + 1]] - c_off[c_brp[i]];
-    atomicMax(maxes + 2, (int)min(n, (uint64_t)0x7FFFFFFF));
+// C's derived row arrays: block-row pointers and value bases for every block row of the full matrix
+// (rows outside [rb, re) are empty in a sharded product).
+__global__ void finish_rows_kernel(const uint32_t* __restrict__ c_brp_local, const uint64_t* __restrict__ row_vbase, int rb, int re,
+                                   int nbr, int32_t* __restrict__ brp, uint32_t* __restrict__ rvb, uint64_t* __restrict__ c_off,
+                                   int64_t c_size, uint64_t c_nnz) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) c_off[c_size] = c_nnz;
+    if (r > nbr) return;
+    if (r < rb) { brp[r] = 0; rvb[r] = 0; }
+    else if (r >= re) { brp[r] = (int32_t)c_size; rvb[r] = (uint32_t)c_nnz; }
+    else { brp[r] = (int32_t)c_brp_local[r - rb]; rvb[r] = (uint32_t)row_vbase[r - rb]; }
 }
 
 }  // namespace bmsp
@@ -515,14 +647,15 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
 
     // ---- scratch
     int2* rowinfo = nullptr; unsigned long long* cand = nullptr; int32_t* small = nullptr;   // small: maxes[3], counter, pad, stats[2]
-    uint32_t* row_count = nullptr;
+    uint32_t *row_count = nullptr, *row_surv = nullptr; uint64_t* row_nnz = nullptr; uint2* surv_list = nullptr;
     bmsp_matrix_s* C = new bmsp_matrix_s();
     C->rows = A->rows; C->cols = Bt->cols; C->dtype = BMSP_F32; C->transposed = 0;
+    C->nbr = (int32_t)ceil_div(C->rows, 8);
     uint32_t *g_bitset = nullptr, *g_wrank = nullptr;
     int status = BMSP_OK;
     auto cleanup = [&]() {
-        dev_free(rowinfo, st); dev_free(cand, st); dev_free(small, st); dev_free(row_count, st);
-        dev_free(g_bitset, st); dev_free(g_wrank, st);
+        dev_free(rowinfo, st); dev_free(cand, st); dev_free(small, st); dev_free(row_count, st); dev_free(row_surv, st);
+        dev_free(row_nnz, st); dev_free(surv_list, st); dev_free(g_bitset, st); dev_free(g_wrank, st);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
     };
     auto fail = [&](int code) { cleanup(); bmsp_destroy(C); return code; };
@@ -533,6 +666,8 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     SG_TRY(dev_alloc_t(&cand, (size_t)nrows + 1, st));
     SG_TRY(dev_alloc_t(&small, 16, st));
     SG_TRY(dev_alloc_t(&row_count, (size_t)nrows + 2, st));
+    SG_TRY(dev_alloc_t(&row_surv, (size_t)nrows + 2, st));
+    SG_TRY(dev_alloc_t(&row_nnz, (size_t)nrows + 2, st));
     SG_CUDA(cudaMemsetAsync(small, 0, 16 * sizeof(int32_t), st));
     int32_t* maxes = small; int32_t* counter = small + 4; unsigned long long* stats = (unsigned long long*)(small + 8);
 
@@ -545,24 +680,24 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     SG_CUDA(cudaStreamSynchronize(st));
     const int max_words = h_small[0];
 
-    // ---- launch shape from averages
+    // ---- launch shape from averages: G lanes share one A block, each lane tests 4 B blocks per step
     const double avgB = Bt->nbr ? (double)Bt->nblk / Bt->nbr : 0.0;
     const double avgA = A->nbr ? (double)A->nblk / A->nbr : 0.0;
     int G = 1;
-    while (G < 32 && G < avgB) G <<= 1;
+    while (G < 32 && G * 4 < avgB) G <<= 1;
     const double avg_cand = avgA * avgB;
     const int T = avg_cand <= 96 ? 32 : (avg_cand <= 2048 ? 128 : 256);
     if (G > T) G = T;
 
     GemmArgs g;
+    memset(&g, 0, sizeof(g));
     g.a_brp = A->brp; g.a_bcol = A->bcol; g.a_bmps = A->bmps; g.a_kmask = A->kmask; g.a_off = A->offsets; g.a_val = (const __half*)A->values;
     g.b_brp = Bt->brp; g.b_bcol = Bt->bcol; g.b_bmps = Bt->bmps; g.b_kmask = Bt->kmask; g.b_off = Bt->offsets; g.b_val = (const __half*)Bt->values;
     g.rowinfo = rowinfo; g.row_begin = rb; g.row_end = re; g.G = G;
     g.cap_words = std::max(1, std::min(max_words, 8192));
     g.cap_c = 0; g.cap_nnz = 0;
-    g.g_bitset = nullptr; g.g_wrank = nullptr; g.max_words = max_words;
-    g.work_counter = counter; g.row_count = row_count; g.maxes = maxes;
-    g.c_brp = nullptr; g.c_keys = nullptr; g.c_bmps = nullptr; g.c_off = nullptr; g.c_val = nullptr; g.stats = stats;
+    g.max_words = max_words;
+    g.work_counter = counter; g.row_count = row_count; g.row_surv = row_surv; g.row_nnz = row_nnz; g.maxes = maxes; g.stats = stats;
 
     if (max_words > g.cap_words) {
         // over-cap rows use per-CTA global scratch; size it for the largest persistent grid (32 CTAs/SM)
@@ -572,43 +707,51 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
         g.g_bitset = g_bitset; g.g_wrank = g_wrank;
     }
 
-    // ---- COUNT
-    int64_t c_size = 0;
+    // ---- COUNT: C blocks and surviving pairs per block row
+    int64_t c_size = 0, n_surv = 0;
     if (nrows > 0) {
         SG_TRY(launch_pass<PASS_COUNT>(g, T, sms, st, nullptr));
         SG_TRY(exclusive_scan_u32(row_count, row_count, nrows, st));
-        uint32_t tot = 0;
-        SG_CUDA(cudaMemcpyAsync(&tot, row_count + nrows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SG_TRY(exclusive_scan_u32(row_surv, row_surv, nrows, st));
+        uint32_t tot[2] = {0, 0};
+        SG_CUDA(cudaMemcpyAsync(&tot[0], row_count + nrows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(&tot[1], row_surv + nrows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaStreamSynchronize(st));
-        c_size = tot;
+        c_size = tot[0]; n_surv = tot[1];
     }
-    if (c_size > 0x7FFFFFFFll) { set_error("C has %lld blocks (> 2^31-1)", (long long)c_size); return fail(BMSP_ERR_TOO_LARGE); }
-    const int max_c = h_small[1];
     unsigned long long h_stats[2];
     memcpy(h_stats, h_small + 8, sizeof(h_stats));
+    if (c_size > 0x7FFFFFFFll || h_stats[1] > 0xFFFFFFFFull) {
+        set_error("product too large for one call: %lld C blocks, %llu surviving pairs (shard A's block rows with brow_begin/brow_end)",
+                  (long long)c_size, h_stats[1]);
+        return fail(BMSP_ERR_TOO_LARGE);
+    }
+    const int max_c = h_small[1];
 
     C->nblk = c_size; C->offsets_len = c_size + 1;
     SG_TRY(dev_alloc_t(&C->keys, (size_t)c_size + 2, st));
     SG_TRY(dev_alloc_t(&C->bmps, (size_t)c_size + 2, st));
     SG_TRY(dev_alloc_t(&C->offsets, (size_t)c_size + 2, st));
-    g.c_brp = (const int32_t*)row_count; g.c_keys = C->keys; g.c_bmps = C->bmps;
+    SG_TRY(dev_alloc_t(&C->bcol, (size_t)c_size + 8, st));
+    SG_TRY(dev_alloc_t(&C->kmask, (size_t)c_size + 16, st));
+    SG_TRY(dev_alloc_t(&C->brp, (size_t)C->nbr + 1 + 8, st));
+    SG_TRY(dev_alloc_t(&C->rvb, (size_t)C->nbr + 1 + 8, st));
+    SG_TRY(dev_alloc_t(&surv_list, (size_t)n_surv + 1, st));
+    g.c_brp = (const int32_t*)row_count; g.c_keys = C->keys; g.c_bmps = C->bmps; g.c_bcol = C->bcol; g.c_kmask = C->kmask;
+    g.c_off = C->offsets; g.surv_list = surv_list;
 
-    // ---- FILL
+    // ---- FILL: pair list, keys, bitmaps, row-relative value offsets
     g.cap_c = std::max(1, std::min(max_c, 4096));
     if (c_size > 0) {
         if (max_c > g.cap_c) SG_CUDA(cudaMemsetAsync(C->bmps, 0, sizeof(uint64_t) * c_size, st));
         SG_TRY(launch_pass<PASS_FILL>(g, T, sms, st, nullptr));
-        popc_kernel<<<(unsigned)ceil_div(c_size, 256), 256, 0, st>>>(C->bmps, C->offsets, c_size);
-        SG_CUDA(cudaGetLastError());
+    } else if (nrows > 0) {
+        SG_CUDA(cudaMemsetAsync(row_nnz, 0, sizeof(uint64_t) * ((size_t)nrows + 1), st));
     }
-    SG_TRY(exclusive_scan_u64(C->offsets, C->offsets, c_size, st));
+    SG_TRY(exclusive_scan_u64(row_nnz, row_nnz, nrows, st));
     uint64_t c_nnz = 0;
-    if (nrows > 0 && c_size > 0) {
-        row_nnz_max_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>((const int32_t*)row_count, C->offsets, nrows, maxes);
-        SG_CUDA(cudaGetLastError());
-    }
-    SG_CUDA(cudaMemcpyAsync(&c_nnz, C->offsets + c_size, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(&c_nnz, row_nnz + nrows, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
     if (c_nnz > 0xFFFFFFFFull) { set_error("C has %llu values (> 2^32-1)", (unsigned long long)c_nnz); return fail(BMSP_ERR_TOO_LARGE); }
@@ -618,25 +761,24 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     if (verbose) SG_CUDA(cudaEventRecord(ev[1], st));
 
     // ---- NUMERIC: scalar lanes for sparse blocks, mma.sync for dense ones (about dA*dB/8 products per pair)
-    g.c_off = C->offsets; g.c_val = (float*)C->values;
+    g.c_val = (float*)C->values;
     const double dA = A->nblk ? (double)A->nnz / A->nblk : 0.0, dB = Bt->nblk ? (double)Bt->nnz / Bt->nblk : 0.0;
     int path = opts ? opts->numeric_path : -1;
     if (path < 0) path = (dA * dB / 8.0 >= 40.0) ? 1 : 0;
     if (c_nnz > 0) {
         if (path == 1) {
-            const int cap_keep = g.cap_c;
             g.cap_c = std::max(1, std::min(max_c, 192));
             if (max_c > g.cap_c) SG_CUDA(cudaMemsetAsync(C->values, 0, (size_t)c_nnz * 4, st));
             SG_TRY(launch_pass<PASS_NUMERIC_MMA>(g, 32, sms, st, nullptr));
-            g.cap_c = cap_keep;
         } else {
             g.cap_nnz = std::max(1, std::min(max_rownnz, 12288));
             if (max_c > g.cap_c || max_rownnz > g.cap_nnz) SG_CUDA(cudaMemsetAsync(C->values, 0, (size_t)c_nnz * 4, st));
             SG_TRY(launch_pass<PASS_NUMERIC>(g, T, sms, st, nullptr));
         }
     }
+    finish_rows_kernel<<<(unsigned)ceil_div(C->nbr + 1, 256), 256, 0, st>>>(row_count, row_nnz, rb, re, C->nbr, C->brp, C->rvb, C->offsets, c_size, c_nnz);
+    SG_CUDA(cudaGetLastError());
     if (verbose) SG_CUDA(cudaEventRecord(ev[2], st));
-    SG_TRY(derive_compact(C, st));
 
     if (info) {
         memset(info, 0, sizeof(*info));

@@ -456,6 +456,7 @@ extern "C" int bmsp_spmv(bmsp_matrix_t A, const void* x, int32_t x_dtype, float*
     if (A->rows == 0) return BMSP_OK;
     if (((uintptr_t)x & 15) || ((uintptr_t)y & 15)) { set_error("bmsp_spmv: x and y must be 16-byte aligned"); return BMSP_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    if (A->spmv_path < 0) BMSP_TRY(plan_spmv(A, st));
     if (A->dtype == BMSP_F16)
         return x_dtype == BMSP_F32 ? launch_spmv<__half, float>(A, (const float*)x, y, st) : launch_spmv<__half, __half>(A, (const __half*)x, y, st);
     return x_dtype == BMSP_F32 ? launch_spmv<float, float>(A, (const float*)x, y, st) : launch_spmv<float, __half>(A, (const __half*)x, y, st);
