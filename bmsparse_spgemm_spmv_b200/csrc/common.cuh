@@ -26,6 +26,7 @@ struct bmsp_matrix_s {
     int32_t* bcol = nullptr;    // [nblk]  block column of each block
     uint32_t* rvb = nullptr;    // [nbr+1] first value index of each block row
     uint8_t* kmask = nullptr;   // [nblk]  OR of the 8 bitmap bytes: inner-dimension (k) occupancy
+    void* pmeta = nullptr;      // [nblk]  uint4 {bitmap lo, hi, block column, value offset}; built by the first SpGEMM that uses this matrix as B
     // SpMV plan (spmv.cu)
     int32_t spmv_path = -2;     // -2 not planned yet, 0 row-tiled (dense-ish blocks), 1 block-parallel (sparse blocks)
     int32_t cap_blk = 0, cap_val = 0;   // per-stage smem capacities of the row-tiled kernel

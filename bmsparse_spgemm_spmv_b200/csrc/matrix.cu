@@ -253,7 +253,7 @@ int bmsp_destroy(bmsp_matrix_t m) {
     cudaStream_t st = 0;
     dev_free(m->keys, st); dev_free(m->bmps, st); dev_free(m->offsets, st); dev_free(m->values, st);
     dev_free(m->brp, st); dev_free(m->bcol, st); dev_free(m->rvb, st); dev_free(m->kmask, st);
-    dev_free(m->work, st); dev_free(m->split_partial, st); dev_free(m->split_rows, st);
+    dev_free(m->work, st); dev_free(m->split_partial, st); dev_free(m->split_rows, st); dev_free(m->pmeta, st);
     delete m;
     return BMSP_OK;
 }

@@ -32,6 +32,7 @@ constexpr int QSLOTS = 192;   // per-warp queue: 64 pairs (uint2) + 32 staged Pa
 struct GemmArgs {
     const int32_t* a_brp; const int32_t* a_bcol; const uint64_t* a_bmps; const uint8_t* a_kmask; const uint64_t* a_off; const __half* a_val;
     const int32_t* b_brp; const int32_t* b_bcol; const uint64_t* b_bmps; const uint8_t* b_kmask; const uint64_t* b_off; const __half* b_val;
+    const uint4* b_pm;         // packed per-B-block metadata {bitmap lo, bitmap hi, block column, value offset}: one sector per surviving pair
     const int2* rowinfo;       // per A block row: x = first C block column of the bit set (multiple of 32), y = words
     int32_t row_begin, row_end;
     int32_t G;                 // lanes cooperating on one A block (power of two <= 32)
@@ -75,6 +76,14 @@ __device__ __forceinline__ int rank64(uint64_t bmp, int p) { return p == 0 ? 0 :
 __global__ void pair_bitmap_test_kernel(const uint64_t* a, const uint64_t* bt, uint64_t* out, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = pair_bitmap(a[i], bt[i]);
+}
+
+__global__ void pack_meta_kernel(const uint64_t* __restrict__ bmps, const int32_t* __restrict__ bcol, const uint64_t* __restrict__ off,
+                                 uint4* __restrict__ pm, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t b = bmps[i];
+    pm[i] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)bcol[i], (uint32_t)off[i]);
 }
 
 // P0: warp per A block row: candidate pairs, and the span [jmin, jmax] of C block columns.
@@ -155,8 +164,9 @@ struct RowCtx {
 
 template <int MODE>
 __device__ __forceinline__ void process_pair(const GemmArgs& g, const RowCtx& r, int a, int b) {
-    const uint64_t abmp = g.a_bmps[a], bbmp = g.b_bmps[b];
-    const int j = g.b_bcol[b] - r.jbase;
+    const uint4 pm = __ldg(g.b_pm + b);
+    const uint64_t abmp = g.a_bmps[a], bbmp = ((uint64_t)pm.y << 32) | pm.x;
+    const int j = (int)pm.z - r.jbase;
     const uint32_t word = r.bitset[j >> 5];
     const int c = (int)r.wrank[j >> 5] + __popc(word & ((1u << (j & 31)) - 1u));
     if (MODE == MODE_FILL) {
@@ -166,7 +176,7 @@ __device__ __forceinline__ void process_pair(const GemmArgs& g, const RowCtx& r,
         if ((uint32_t)(pb >> 32)) atomicOr(w + 1, (unsigned int)(pb >> 32));
     } else {
         const __half* av = g.a_val + g.a_off[a];
-        const __half* bv = g.b_val + g.b_off[b];
+        const __half* bv = g.b_val + pm.w;
         uint64_t cb; float* dst;
         if (r.acc) { cb = r.cbmp[c]; dst = r.acc + r.coff[c]; }
         else { cb = g.c_bmps[r.c0 + c]; dst = g.c_val + g.c_off[r.c0 + c]; }
@@ -689,8 +699,14 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     const int T = avg_cand <= 96 ? 32 : (avg_cand <= 2048 ? 128 : 256);
     if (G > T) G = T;
 
+    if (!Bt->pmeta && Bt->nblk > 0) {      // built once per B operand, reused by later products
+        SG_TRY(dev_alloc((void**)&Bt->pmeta, sizeof(uint4) * (size_t)Bt->nblk, st));
+        pack_meta_kernel<<<(unsigned)ceil_div(Bt->nblk, 256), 256, 0, st>>>(Bt->bmps, Bt->bcol, Bt->offsets, (uint4*)Bt->pmeta, Bt->nblk);
+        SG_CUDA(cudaGetLastError());
+    }
     GemmArgs g;
     memset(&g, 0, sizeof(g));
+    g.b_pm = (const uint4*)Bt->pmeta;
     g.a_brp = A->brp; g.a_bcol = A->bcol; g.a_bmps = A->bmps; g.a_kmask = A->kmask; g.a_off = A->offsets; g.a_val = (const __half*)A->values;
     g.b_brp = Bt->brp; g.b_bcol = Bt->bcol; g.b_bmps = Bt->bmps; g.b_kmask = Bt->kmask; g.b_off = Bt->offsets; g.b_val = (const __half*)Bt->values;
     g.rowinfo = rowinfo; g.row_begin = rb; g.row_end = re; g.G = G;
