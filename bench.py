@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GRID = 4096
+_OUT = sys.stdout
 SPGEMM_N, SPGEMM_K = 1_000_000, 16
 
 
@@ -135,7 +136,7 @@ def reference_arm(args):
             "config": {"workload": f"poisson5pt {GRID}x{GRID} CSR SpMV on host memory (cusp::multiply host path), one slab per step"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 def spgemm_bench(B, G, torch, O, steps=3):
@@ -189,6 +190,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # native libraries (NCCL's version banner) print to fd 1: keep the real stdout for the one JSON line only
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -347,7 +352,7 @@ def main():
             torch.cuda.empty_cache()
             line["spgemm"] = spgemm_bench(B, G, torch, O)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

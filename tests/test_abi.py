@@ -46,3 +46,14 @@ def test_compute_fails_loudly_without_gpu():
     code = L.lib().bmsp_create_from_csr(1, 1, ctypes.c_int64(1), p(rp), p(ci), p(v), L.F32, L.HOST, 0, L.F16, None, ctypes.byref(h))
     assert code == 2, "without a CUDA device the library must fail with BMSP_ERR_CUDA, not fall back"
     assert b"CUDA" in L.lib().bmsp_last_error()
+
+
+def test_cpp_shim_headers_compile(tmp_path):
+    """include/bmSpMatrix.h, reader.h, CSRMatrix.h are plain C++ over the C ABI: they must compile without CUDA headers."""
+    import subprocess
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "bmSpMatrix.h"\n#include "reader.h"\n#include "CSRMatrix.h"\n'
+                   'int f(bmSpMatrix<float>& a, float* v, float* u) { bmSparse_SpMV<float, float>(a, v, u, false); return a.block_num; }\n')
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

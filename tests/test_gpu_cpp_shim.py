@@ -1,0 +1,34 @@
+"""GPU: the C++ shim (include/bmSpMatrix.h / reader.h / CSRMatrix.h) driving the library the way the reference's mains do."""
+import os
+import subprocess
+
+import pytest
+
+from tests.util import load_golden
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _write_mtx(path, n, rows, cols, vals):
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n%\n")
+        f.write(f"{n} {n} {len(rows)}\n")
+        for r, c, v in zip(rows, cols, vals):
+            f.write(f"{r + 1} {c + 1} {v}\n")
+
+
+def test_shim_runs_reference_style_main(tmp_path):
+    exe = os.path.join(ROOT, "tools", "_build", "shim_smoke")
+    if not os.path.exists(exe):
+        pytest.skip("tools/_build/shim_smoke not built")
+    g = load_golden("ragusa16.json")
+    a, b = str(tmp_path / "A.mtx"), str(tmp_path / "B.mtx")
+    _write_mtx(a, 24, g["A"]["rows"], g["A"]["cols"], g["A"]["vals"])
+    _write_mtx(b, 24, g["B"]["rows"], g["B"]["cols"], g["B"]["vals"])
+    out = subprocess.run([exe, a, b], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.splitlines()
+    assert "C blocks: 9" in lines and "C nnz: 255" in lines
+    assert f"SpMV sum: {sum(g['spmv_ones']):.1f}" in lines
+    assert "mmread: 24 24 81 blocks 9" in lines and "CSR C nnz: 255" in lines
