@@ -29,7 +29,12 @@ struct bmsp_matrix_s {
     void* pmeta = nullptr;      // [nblk]  uint4 {bitmap lo, hi, block column, value offset}; built by the first SpGEMM that uses this matrix as B
     // SpMV plan (spmv.cu)
     int32_t spmv_path = -2;     // -2 not planned yet, 0 row-tiled (dense-ish blocks), 1 block-parallel (sparse blocks)
-    int32_t cap_blk = 0, cap_val = 0;   // per-stage smem capacities of the row-tiled kernel
+    int32_t cap_blk = 0, cap_val = 0;   // per-tile smem capacities of the row-tiled kernels
+    int32_t cap_lines = 0;      // staged x lines per tile (tile plan)
+    void* tile_rowpair = nullptr;   // [nbr+1] int2 (block_row_ptr, first value) zipped for one bulk copy per tile
+    void* tile_desc = nullptr;  // [ntiles] TileDesc (spmv.cu): block / value / x-line ranges of every tile of 64 block rows
+    uint32_t* tile_lines = nullptr;   // [nblk] distinct x lines (32 columns) of every tile, stored from the tile's first block index
+    uint16_t* tile_xoff = nullptr;    // [nblk] per block: element offset of its 8-column x segment inside the tile's staged lines
     int32_t* work = nullptr;    // block-parallel work items (int4 per item)
     int32_t n_work = 0, n_split = 0;
     float* split_partial = nullptr;

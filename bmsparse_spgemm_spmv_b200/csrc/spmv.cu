@@ -21,6 +21,7 @@
 //       a deterministic fix-up kernel.
 #include "common.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 namespace bmsp {
 
@@ -291,6 +292,369 @@ __global__ void __launch_bounds__(SPMV_THREADS, MINB) spmv_rowtile_kernel(SpmvAr
     else for (int q = 0; q < 4; q++) if (row + q < a.rows) y[row + q] = acc[q];
 }
 
+
+// ===================================================================================== path 0, tile plan
+// Built once per matrix (plan_spmv): for every tile of RT block rows, the sorted distinct x "lines" (32 columns
+// = 4 block columns = 128 B of fp32 x) its blocks touch, and per block a 16-bit offset of its 8-column x segment
+// inside the tile's staged copy of those lines.  The kernel then never reads block_col: it streams bitmaps
+// (8 B), x offsets (2 B) and values per block, gathers each distinct x line ONCE per tile with coalesced
+// 16-byte loads (8 threads per line) and serves every per-value x read from shared memory.  Staged lines
+// have a pitch of 34 elements: when the 16 block rows of a warp read the same column of consecutive block
+// columns (stencils, bands) the 16 addresses fall into 16 different banks.
+constexpr int XL_STRIDE = 33;      // staged x line pitch, elements (32 + 1 skew)
+constexpr int PLAN_MAXB = 2048;    // blocks per tile the planner sorts in shared memory
+constexpr int XL_MAX = 1900;       // distinct lines per tile (16-bit element offsets)
+
+struct __align__(16) TileDesc { int32_t p0, nb; uint32_t v0; int32_t nv, nl, flags, pad0, pad1; };   // 32 bytes
+
+__global__ void __launch_bounds__(256) tile_plan_kernel(const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
+                                                        const uint32_t* __restrict__ rvb, int nbr, int ncols, TileDesc* __restrict__ desc,
+                                                        uint32_t* __restrict__ lines, uint16_t* __restrict__ xoff,
+                                                        unsigned long long* __restrict__ stats) {
+    __shared__ uint32_t s_key[PLAN_MAXB];
+    __shared__ uint32_t s_uniq[PLAN_MAXB];
+    __shared__ uint32_t s_w[9];
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int r0 = t * RT, r1 = min(r0 + RT, nbr);
+    const int p0 = brp[r0], nb = brp[r1] - p0;
+    const uint32_t v0 = rvb[r0], v1 = rvb[r1];
+    TileDesc d;
+    d.p0 = p0; d.nb = nb; d.v0 = v0; d.nv = (int32_t)(v1 - v0); d.nl = 0; d.flags = 0; d.pad0 = d.pad1 = 0;
+    if (nb > PLAN_MAXB) {          // too many blocks to plan: the kernel reads this tile straight from global memory
+        if (tid == 0) { desc[t] = d; atomicAdd(stats + 4, 1ull); }
+        return;
+    }
+    int n2 = 32;
+    while (n2 < nb) n2 <<= 1;
+    for (int i = tid; i < n2; i += 256) s_key[i] = i < nb ? ((uint32_t)bcol[p0 + i] >> 2) : 0xFFFFFFFFu;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n2; i += 256) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint32_t a = s_key[i], b = s_key[ixj];
+                    if ((a > b) == ((i & k) == 0)) { s_key[i] = b; s_key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // distinct keys, order kept: thread t owns `per` consecutive sorted slots
+    const int per = n2 >= 256 ? n2 / 256 : 1;
+    const int i0 = tid * per, i1 = min(i0 + per, nb);
+    uint32_t cnt = 0;
+    for (int i = i0; i < i1; i++) cnt += (i == 0 || s_key[i] != s_key[i - 1]) ? 1u : 0u;
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int w = 0; w < 8; w++) { const uint32_t c = s_w[w]; s_w[w] = run; run += c; }
+        s_w[8] = run;
+    }
+    __syncthreads();
+    uint32_t run = s_w[wid] + inc - cnt;
+    for (int i = i0; i < i1; i++)
+        if (i == 0 || s_key[i] != s_key[i - 1]) s_uniq[run++] = s_key[i];
+    const int nl = (int)s_w[8];
+    __syncthreads();
+    for (int j = tid; j < nl; j += 256) lines[p0 + j] = s_uniq[j];
+    const bool ok = nl <= XL_MAX;
+    if (ok)
+        for (int i = tid; i < nb; i += 256) {
+            const uint32_t c = (uint32_t)bcol[p0 + i], line = c >> 2;
+            int lo = 0, hi = nl;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_uniq[mid] < line) lo = mid + 1; else hi = mid;
+            }
+            xoff[p0 + i] = (uint16_t)(lo * XL_STRIDE + (int)(c & 3u) * 8);
+        }
+    if (tid == 0) {
+        // flags: bit 0 = planned (x offsets valid), bit 1 = the last line reaches past the last column (guarded gather)
+        d.nl = nl; d.flags = (ok ? 1 : 0) | ((nl > 0 && (uint64_t)s_uniq[nl - 1] * 32u + 32u > (uint64_t)ncols) ? 2 : 0);
+        desc[t] = d;
+        atomicMax(stats + 0, (unsigned long long)nb);
+        atomicMax(stats + 1, (unsigned long long)(v1 - v0));
+        atomicMax(stats + 2, (unsigned long long)nl);
+        atomicAdd(stats + 3, (unsigned long long)nl);
+        if (!ok) atomicAdd(stats + 4, 1ull);
+    }
+}
+
+// shared-memory carve-up of spmv_tile_kernel (cap_blk and cap_val are multiples of 8); computed on the host
+struct TileSmem { uint32_t xo, val, row, xs, bar, total; };
+inline TileSmem tile_smem(int cap_blk, int cap_val, int cap_lines, int vsize, int xsize) {
+    TileSmem s;
+    s.xo = (uint32_t)(cap_blk + 2) * 8;
+    s.val = s.xo + (uint32_t)(cap_blk + 16) * 2;
+    s.row = s.val + (uint32_t)(cap_val + 16) * vsize;
+    s.xs = s.row + (RT + 2) * 8;
+    s.bar = (s.xs + (uint32_t)cap_lines * XL_STRIDE * xsize + 15u) & ~15u;
+    s.total = s.bar + 16;
+    return s;
+}
+
+template <typename T>
+struct TileArgs {
+    const uint64_t* bmps; const int32_t* bcol; const T* values; const int2* rowpair;   // rowpair[r] = (block_row_ptr[r], first value of row r)
+    const TileDesc* desc; const uint32_t* lines; const uint16_t* xoff;
+    int32_t rows, nbr, cols, cap_blk, cap_val, cap_lines;
+    TileSmem so;
+};
+
+__global__ void zip_rows_kernel(const int32_t* __restrict__ brp, const uint32_t* __restrict__ rvb, int n, int2* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_int2(brp[i], (int)rvb[i]);
+}
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(dst), "l"(src), "n"(BYTES), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Two 8-bit row masks b0, b1 of one bitmap half (left in place: row r of the half occupies bits 31-8r..24-8r)
+// advance together: every round takes the highest set bit p of each mask, multiplies the row's next value
+// (shared address va + round * sizeof(T)) with x[column] (shared address xb - p * sizeof(X) - 8 r sizeof(X),
+// the row term folded into the load's immediate) and clears the bit.  The whole walk is one PTX block so that
+// the predicates stay in predicate registers from round to round: per value FLO, IMAD, 2 LDS, BMSK, LOP3,
+// (cvt,) FFMA, and no branch other than the early exit once both masks are empty.  Value loads are not
+// predicated (their addresses stay inside the staged tile), x loads and the FMAs are.
+#define BMSP_RND(OFF, VLD, VC0, VC1, XLD, XC0, XC1, XMUL, XA, XB)                                        \
+    "bfind.u32 p0, %2;\n\tbfind.u32 p1, %3;\n\t"                                                          \
+    "mad.lo.s32 a0, p0, " XMUL ", %6;\n\tmad.lo.s32 a1, p1, " XMUL ", %6;\n\t"                            \
+    VLD "0, [%4+" #OFF "];\n\t" VLD "1, [%5+" #OFF "];\n\t"                                               \
+    "@q0 " XLD "0, [a0+" XA "];\n\t@q1 " XLD "1, [a1+" XB "];\n\t"                                        \
+    "bmsk.clamp.b32 m0, p0, 1;\n\tbmsk.clamp.b32 m1, p1, 1;\n\t" VC0 VC1 XC0 XC1                          \
+    "@q0 fma.rn.f32 %0, f0, x0, %0;\n\t@q1 fma.rn.f32 %1, f1, x1, %1;\n\t"                                \
+    "not.b32 m0, m0;\n\tnot.b32 m1, m1;\n\tand.b32 %2, %2, m0;\n\tand.b32 %3, %3, m1;\n\t"                \
+    "setp.ne.u32 q0, %2, 0;\n\tsetp.ne.u32 q1, %3, 0;\n\tor.pred qa, q0, q1;\n\t@!qa bra DONE;\n\t"
+#define BMSP_PAIR(O0, O1, O2, O3, O4, O5, O6, O7, VLD, VC0, VC1, XLD, XC0, XC1, XMUL, XA, XB)            \
+    asm("{\n\t.reg .pred q0, q1, qa;\n\t.reg .u32 p0, p1, m0, m1, a0, a1, h0, h1, g0, g1;\n\t"            \
+        ".reg .f32 x0, x1, f0, f1;\n\t.reg .b16 lo, hi;\n\t"                                              \
+        "setp.ne.u32 q0, %2, 0;\n\tsetp.ne.u32 q1, %3, 0;\n\tor.pred qa, q0, q1;\n\t@!qa bra DONE;\n\t"   \
+        BMSP_RND(O0, VLD, VC0, VC1, XLD, XC0, XC1, XMUL, XA, XB) BMSP_RND(O1, VLD, VC0, VC1, XLD, XC0, XC1, XMUL, XA, XB)  \
+        BMSP_RND(O2, VLD, VC0, VC1, XLD, XC0, XC1, XMUL, XA, XB) BMSP_RND(O3, VLD, VC0, VC1, XLD, XC0, XC1, XMUL, XA, XB)  \
+        BMSP_RND(O4, VLD, VC0, VC1, XLD, XC0, XC1, XMUL, XA, XB) BMSP_RND(O5, VLD, VC0, VC1, XLD, XC0, XC1, XMUL, XA, XB)  \
+        BMSP_RND(O6, VLD, VC0, VC1, XLD, XC0, XC1, XMUL, XA, XB) BMSP_RND(O7, VLD, VC0, VC1, XLD, XC0, XC1, XMUL, XA, XB)  \
+        "DONE:\n\t}"                                                                                      \
+        : "+f"(acc0), "+f"(acc1), "+r"(b0), "+r"(b1) : "r"(va0), "r"(va1), "r"(xb))
+#define BMSP_CVT16(dst, src) "mov.b32 {lo, hi}, " src ";\n\tcvt.f32.f16 " dst ", lo;\n\t"
+// PAIR 0: rows 0,1 of the half (x immediates 0 and -8 columns); PAIR 1: rows 2,3 (-16 and -24 columns)
+template <typename T, typename X, int PAIR> struct RowPair;
+#define BMSP_ROWPAIR(TT, XX, PP, ...)                                                                                             \
+    template <> struct RowPair<TT, XX, PP> {                                                                                      \
+        static __device__ __forceinline__ void run(float& acc0, float& acc1, uint32_t b0, uint32_t b1, uint32_t va0, uint32_t va1, \
+                                                   uint32_t xb) {                                                                 \
+            BMSP_PAIR(__VA_ARGS__);                                                                                               \
+        }                                                                                                                         \
+    };
+#define BMSP_V16 0, 2, 4, 6, 8, 10, 12, 14, "ld.shared.u16 h", BMSP_CVT16("f0", "h0"), BMSP_CVT16("f1", "h1")
+#define BMSP_V32 0, 4, 8, 12, 16, 20, 24, 28, "ld.shared.f32 f", "", ""
+#define BMSP_X32 "ld.shared.f32 x", "", "", "-4"
+#define BMSP_X16 "ld.shared.u16 g", BMSP_CVT16("x0", "g0"), BMSP_CVT16("x1", "g1"), "-2"
+BMSP_ROWPAIR(__half, float, 0, BMSP_V16, BMSP_X32, "0", "-32")
+BMSP_ROWPAIR(__half, float, 1, BMSP_V16, BMSP_X32, "-64", "-96")
+BMSP_ROWPAIR(__half, __half, 0, BMSP_V16, BMSP_X16, "0", "-16")
+BMSP_ROWPAIR(__half, __half, 1, BMSP_V16, BMSP_X16, "-32", "-48")
+BMSP_ROWPAIR(float, float, 0, BMSP_V32, BMSP_X32, "0", "-32")
+BMSP_ROWPAIR(float, float, 1, BMSP_V32, BMSP_X32, "-64", "-96")
+BMSP_ROWPAIR(float, __half, 0, BMSP_V32, BMSP_X16, "0", "-16")
+BMSP_ROWPAIR(float, __half, 1, BMSP_V32, BMSP_X16, "-32", "-48")
+#undef BMSP_RND
+#undef BMSP_PAIR
+#undef BMSP_CVT16
+#undef BMSP_ROWPAIR
+#undef BMSP_V16
+#undef BMSP_V32
+#undef BMSP_X32
+#undef BMSP_X16
+
+// The blocks of one block row seen by the thread that owns bitmap half h (rows 4h..4h+3).  Everything lives in
+// shared memory: bitmaps at a_bm, 16-bit x offsets at a_xo, the row's values from a_v on; xs31 = staged x + 31
+// elements.
+template <typename T, typename X>
+__device__ __forceinline__ void tile_half_row(uint32_t a_bm, uint32_t a_xo, uint32_t a_v, int nb, const int h, const uint32_t xs31,
+                                              float (&acc)[4]) {
+    constexpr uint32_t SV = sizeof(T), SX = sizeof(X);
+    const uint32_t hm = 0u - (uint32_t)h;
+#pragma unroll 1
+    for (int i = 0; i < nb; i++) {
+        const uint2 w2 = lds_v2(a_bm);                  // .y = rows 0-3, .x = rows 4-7
+        const uint32_t xo = lds_u16(a_xo);
+        a_bm += 8; a_xo += 2;
+        const uint32_t nhi = __popc(w2.y), nlo = __popc(w2.x);
+        const uint32_t w = (w2.x & hm) | (w2.y & ~hm);
+        const uint32_t va0 = a_v + (nhi & hm) * SV;
+        a_v += (nhi + nlo) * SV;
+        if (w) {
+            const uint32_t xb = xs31 + xo * SX;
+            const uint32_t b0 = w & 0xFF000000u, b1 = w & 0x00FF0000u, b2 = w & 0x0000FF00u, b3 = w & 0x000000FFu;
+            const uint32_t va1 = va0 + __popc(b0) * SV, va2 = va1 + __popc(b1) * SV, va3 = va2 + __popc(b2) * SV;
+            RowPair<T, X, 0>::run(acc[0], acc[1], b0, b1, va0, va1, xb);
+            RowPair<T, X, 1>::run(acc[2], acc[3], b2, b3, va2, va3, xb);
+        }
+    }
+}
+
+// The blocks of one whole block row (all 8 matrix rows) walked by one thread: the per-block bookkeeping is paid
+// once per block instead of once per bitmap half.
+template <typename T, typename X>
+__device__ __forceinline__ void tile_block_row(uint32_t a_bm, uint32_t a_xo, uint32_t a_v, int nb, const uint32_t xs31, float (&acc)[8]) {
+    constexpr uint32_t SV = sizeof(T), SX = sizeof(X);
+#pragma unroll 1
+    for (int i = 0; i < nb; i++) {
+        const uint2 w2 = lds_v2(a_bm);                  // .y = rows 0-3, .x = rows 4-7
+        const uint32_t xo = lds_u16(a_xo);
+        a_bm += 8; a_xo += 2;
+        const uint32_t hi = w2.y, lo = w2.x;
+        const uint32_t xb = xs31 + xo * SX;
+        const uint32_t b0 = hi & 0xFF000000u, b1 = hi & 0x00FF0000u, b2 = hi & 0x0000FF00u, b3 = hi & 0x000000FFu;
+        const uint32_t b4 = lo & 0xFF000000u, b5 = lo & 0x00FF0000u, b6 = lo & 0x0000FF00u, b7 = lo & 0x000000FFu;
+        const uint32_t va0 = a_v, va1 = va0 + __popc(b0) * SV, va2 = va1 + __popc(b1) * SV, va3 = va2 + __popc(b2) * SV;
+        const uint32_t va4 = va3 + __popc(b3) * SV, va5 = va4 + __popc(b4) * SV, va6 = va5 + __popc(b5) * SV, va7 = va6 + __popc(b6) * SV;
+        a_v = va7 + __popc(b7) * SV;
+        if (hi) {
+            RowPair<T, X, 0>::run(acc[0], acc[1], b0, b1, va0, va1, xb);
+            RowPair<T, X, 1>::run(acc[2], acc[3], b2, b3, va2, va3, xb);
+        }
+        if (lo) {
+            RowPair<T, X, 0>::run(acc[4], acc[5], b4, b5, va4, va5, xb);
+            RowPair<T, X, 1>::run(acc[6], acc[7], b6, b7, va6, va7, xb);
+        }
+    }
+}
+
+template <typename X> __device__ __forceinline__ void sts_x(uint32_t a, X v);
+template <> __device__ __forceinline__ void sts_x<float>(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+template <> __device__ __forceinline__ void sts_x<__half>(uint32_t a, __half v) {
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(__half_as_ushort(v)) : "memory");
+}
+template <typename X> struct alignas(4 * sizeof(X)) XQuad { X e[4]; };
+
+// One CTA per tile of RT block rows, TPR threads per block row (1: a thread owns all 8 matrix rows of its block
+// row; 2: one thread per 32-bit bitmap half).  Every thread reads the 32-byte tile descriptor; thread 0 arms the
+// mbarrier and issues the bulk copies (row pointers, bitmaps, x offsets, values) while all threads gather the
+// tile's distinct x lines (coalesced 16-byte loads, stored at a 33-element pitch); latency is hidden by the CTAs
+// resident per SM, each in a different phase.
+template <typename T, typename X, int TPR, int MINB>
+__global__ void __launch_bounds__(RT * TPR, MINB) spmv_tile_kernel(const TileArgs<T> a, const X* __restrict__ x, float* __restrict__ y) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int VA = 16 / sizeof(T);   // values per 16 bytes
+    constexpr int NT = RT * TPR;
+    constexpr int LPI = NT / 8;          // x lines per gather step (8 threads per line)
+    constexpr int GB = TPR == 1 ? 8 : 4; // gather steps in flight
+    constexpr uint32_t SX = sizeof(X);
+    const int tid = threadIdx.x, t = blockIdx.x;
+    const uint32_t sbase = smem_u32(smem);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + a.so.bar);
+
+    const int4* dp = reinterpret_cast<const int4*>(a.desc + t);
+    const int4 d0 = __ldg(dp);
+    const int2 d1 = __ldg(reinterpret_cast<const int2*>(dp + 1));
+    const int p0 = d0.x, nb = d0.y, nv = d0.w, nl = d1.x;
+    const uint32_t v0 = (uint32_t)d0.z, v0a = v0 & ~(uint32_t)(VA - 1);
+    const bool staged = (d1.y & 1) && nb <= a.cap_blk && nv <= a.cap_val && nl <= a.cap_lines;
+    const int r0 = t * RT, nrow = min(RT, a.nbr - r0);
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        const uint32_t nrb = (uint32_t)((nrow + 1 + 1) & ~1) * 8;
+        const int p0a = p0 & ~1, p0x = p0 & ~7;
+        uint32_t n8 = 0, n2 = 0, nvb = 0;
+        if (staged && nb > 0) {
+            n8 = (uint32_t)((p0 + nb - p0a + 1) & ~1) * 8;
+            n2 = (uint32_t)((p0 + nb - p0x + 7) & ~7) * 2;
+            nvb = ((v0 + (uint32_t)nv - v0a + (uint32_t)(VA - 1)) & ~(uint32_t)(VA - 1)) * (uint32_t)sizeof(T);
+        }
+        mbar_arrive_expect_tx(bar, n8 + n2 + nvb + nrb);
+        bulk_g2s(smem + a.so.row, a.rowpair + r0, nrb, bar);
+        if (n8) bulk_g2s(smem, a.bmps + p0a, n8, bar);
+        if (n2) bulk_g2s(smem + a.so.xo, a.xoff + p0x, n2, bar);
+        if (nvb) bulk_g2s(smem + a.so.val, a.values + v0a, nvb, bar);
+    }
+    if (staged) {
+        // x lines -> shared: 8 threads per line (4 elements each), GB steps of LPI lines in flight before the first store
+        const uint32_t j4 = (uint32_t)(tid & 7) * 4u;
+        const int l0 = tid >> 3;
+        const uint32_t* lp = a.lines + p0 + l0;
+        uint32_t dst = sbase + a.so.xs + ((uint32_t)l0 * XL_STRIDE + j4) * SX;
+        const X* xj = x + j4;
+        if (!(d1.y & 2)) {
+            for (int l = l0; l < nl; l += LPI * GB) {
+                XQuad<X> buf[GB];
+#pragma unroll
+                for (int g = 0; g < GB; g++)
+                    if (l + g * LPI < nl) buf[g] = *reinterpret_cast<const XQuad<X>*>(xj + (size_t)__ldg(lp + g * LPI) * 32u);
+#pragma unroll
+                for (int g = 0; g < GB; g++)
+                    if (l + g * LPI < nl) {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) sts_x<X>(dst + (uint32_t)(g * LPI * XL_STRIDE + e) * SX, buf[g].e[e]);
+                    }
+                lp += LPI * GB;
+                dst += (uint32_t)(LPI * GB * XL_STRIDE) * SX;
+            }
+        } else {      // the tile's last line reaches past the last column: element-wise guarded loads
+            for (int l = l0; l < nl; l += LPI) {
+                const uint32_t col = __ldg(lp) * 32u + j4;
+#pragma unroll
+                for (int e = 0; e < 4; e++) sts_x<X>(dst + e * SX, col + e < (uint32_t)a.cols ? x[col + e] : X(0.f));
+                lp += LPI;
+                dst += (uint32_t)(LPI * XL_STRIDE) * SX;
+            }
+        }
+    }
+    __syncthreads();                 // barrier initialised and armed, x lines visible
+    mbar_wait(bar, 0);
+
+    const int lbr = tid / TPR, h = tid % TPR;
+    constexpr int NR = 8 / TPR;      // matrix rows per thread
+    const int row = (r0 + lbr) * 8 + h * NR;
+    if (lbr >= nrow || row >= a.rows) return;
+    float acc[NR];
+#pragma unroll
+    for (int q = 0; q < NR; q++) acc[q] = 0.f;
+    const uint2 rp = lds_v2(sbase + a.so.row + 8u * lbr);          // (first block, first value) of this block row
+    const uint32_t pe = lds_u32(sbase + a.so.row + 8u * lbr + 8u);
+    const uint32_t pb = rp.x, kv = rp.y;
+    if (staged) {
+        const uint32_t rel = pb - (uint32_t)p0;
+        const uint32_t a_bm = sbase + ((uint32_t)(p0 & 1) + rel) * 8u, a_xo = sbase + a.so.xo + ((uint32_t)(p0 & 7) + rel) * 2u;
+        const uint32_t a_v = sbase + a.so.val + (kv - v0a) * (uint32_t)sizeof(T), xs31 = sbase + a.so.xs + 31u * SX;
+        if constexpr (TPR == 2) tile_half_row<T, X>(a_bm, a_xo, a_v, (int)(pe - pb), h, xs31, acc);
+        else tile_block_row<T, X>(a_bm, a_xo, a_v, (int)(pe - pb), xs31, acc);
+    } else if constexpr (TPR == 2) {
+        half_block_row<T, X>(a.bmps, a.bcol, a.values, (int)pb, (int)pe, kv, h, x, acc);
+    } else {
+        float lo4[4] = {0.f, 0.f, 0.f, 0.f}, hi4[4] = {0.f, 0.f, 0.f, 0.f};
+        half_block_row<T, X>(a.bmps, a.bcol, a.values, (int)pb, (int)pe, kv, 0, x, lo4);
+        half_block_row<T, X>(a.bmps, a.bcol, a.values, (int)pb, (int)pe, kv, 1, x, hi4);
+#pragma unroll
+        for (int q = 0; q < 4; q++) { acc[q] = lo4[q]; acc[4 + q] = hi4[q]; }
+    }
+    float* yr = y + row;
+    if (row + NR <= a.rows) {
+#pragma unroll
+        for (int q = 0; q < NR; q += 4) *reinterpret_cast<float4*>(yr + q) = make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NR; q++) if (row + q < a.rows) yr[q] = acc[q];
+    }
+}
+
 // ------------------------------------------------------------------------------------ path 1
 // work item: x = block row, y = first block, z = end block, w = 1 when the block row is sliced
 template <typename T, typename X>
@@ -376,10 +740,52 @@ __global__ void work_fill_kernel(const int32_t* __restrict__ brp, int nbr, const
     }
 }
 
+static int spmv_variant() {
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("BMSP_SPMV_VARIANT"); variant = e ? atoi(e) : 0; }
+    return variant;
+}
+
+// path 0 plan: tile descriptors, x lines and per-block x offsets; shared-memory capacities from the tile maxima
+// when they fit the per-CTA budget, else from the averages (larger tiles are then read from global memory).
+static int plan_tiles(bmsp_matrix_s* m, cudaStream_t st) {
+    const int ntiles = (int)ceil_div(m->nbr, RT);
+    unsigned long long* stats = nullptr;
+    BMSP_TRY(dev_alloc((void**)&m->tile_desc, sizeof(TileDesc) * (size_t)ntiles, st));
+    BMSP_TRY(dev_alloc_t(&m->tile_lines, (size_t)m->nblk + 8, st));
+    BMSP_TRY(dev_alloc_t(&m->tile_xoff, (size_t)m->nblk + 16, st));
+    BMSP_TRY(dev_alloc((void**)&m->tile_rowpair, sizeof(int2) * ((size_t)m->nbr + 1 + 8), st));
+    zip_rows_kernel<<<(unsigned)ceil_div(m->nbr + 1, 256), 256, 0, st>>>(m->brp, m->rvb, m->nbr + 1, (int2*)m->tile_rowpair);
+    BMSP_KERNEL_CHECK();
+    BMSP_TRY(dev_alloc_t(&stats, 8, st));
+    BMSP_CUDA(cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), st));
+    tile_plan_kernel<<<ntiles, 256, 0, st>>>(m->brp, m->bcol, m->rvb, m->nbr, m->cols, (TileDesc*)m->tile_desc, m->tile_lines, m->tile_xoff, stats);
+    BMSP_KERNEL_CHECK();
+    unsigned long long h[8];
+    BMSP_CUDA(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+    BMSP_CUDA(cudaStreamSynchronize(st));
+    dev_free(stats, st);
+    const int vsize = m->dtype == BMSP_F16 ? 2 : 4;
+    auto up8 = [](long long v) { return (int)((v + 7) & ~7ll); };
+    int cb = up8((long long)h[0]), cv = up8((long long)h[1]), cl = (int)h[2];
+    const size_t budget = 40 * 1024;
+    if (tile_smem(cb, cv, cl, vsize, 4).total > budget) {
+        const double ab = (double)m->nblk / ntiles, av = (double)m->nnz / ntiles, al = (double)h[3] / ntiles;
+        cb = std::min(cb, up8((long long)(ab * 1.25) + 16)); cv = std::min(cv, up8((long long)(av * 1.25) + 64));
+        cl = std::min(cl, (int)(al * 1.25) + 4);
+        while (tile_smem(cb, cv, cl, vsize, 4).total > budget && (cb > 64 || cv > 256 || cl > 16)) {
+            cb = std::max(64, up8(cb * 3 / 4)); cv = std::max(256, up8(cv * 3 / 4)); cl = std::max(16, cl * 3 / 4);
+        }
+    }
+    m->cap_blk = std::max(cb, 8); m->cap_val = std::max(cv, 8); m->cap_lines = std::max(cl, 1);
+    return BMSP_OK;
+}
+
 int plan_spmv(bmsp_matrix_s* m, cudaStream_t st) {
     if (m->transposed || m->nbr == 0) { m->spmv_path = -1; return BMSP_OK; }
     const double per_blk = m->nblk ? (double)m->nnz / (double)m->nblk : 0.0;
     m->spmv_path = per_blk >= 2.5 ? 0 : 1;
+    if (m->spmv_path == 0 && spmv_variant() < 2) return plan_tiles(m, st);
     if (m->spmv_path == 0) {
         const int vsize = m->dtype == BMSP_F16 ? 2 : 4;
         double ab = (double)m->nblk / m->nbr * RT, av = (double)m->nnz / m->nbr * RT;
@@ -413,17 +819,36 @@ int plan_spmv(bmsp_matrix_s* m, cudaStream_t st) {
 
 template <typename T, typename X>
 static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st) {
+    if (A->spmv_path == 0 && spmv_variant() < 2) {
+        TileArgs<T> a;
+        a.bmps = A->bmps; a.bcol = A->bcol; a.values = (const T*)A->values; a.rowpair = (const int2*)A->tile_rowpair;
+        a.desc = (const TileDesc*)A->tile_desc; a.lines = A->tile_lines; a.xoff = A->tile_xoff;
+        a.rows = A->rows; a.nbr = A->nbr; a.cols = A->cols; a.cap_blk = A->cap_blk; a.cap_val = A->cap_val; a.cap_lines = A->cap_lines;
+        a.so = tile_smem(a.cap_blk, a.cap_val, a.cap_lines, sizeof(T), sizeof(X));
+        const size_t smem = a.so.total;
+        // default: one thread per bitmap half (128-thread CTAs); BMSP_SPMV_VARIANT=1: one thread per block row (64-thread CTAs).
+        // Measured on P4096: 92.7 us vs 103.5 us (fewer instructions, but too few warps to hide the staging latency).
+        void (*kern)(TileArgs<T>, const X*, float*) = spmv_tile_kernel<T, X, 2, 12>;
+        int nthreads = 2 * RT;
+        if (spmv_variant() == 1) { kern = spmv_tile_kernel<T, X, 1, 14>; nthreads = RT; }
+        static size_t configured = 0;
+        static void* configured_for = nullptr;
+        if (configured < smem || configured_for != (void*)kern) {
+            BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+            BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            configured = smem; configured_for = (void*)kern;
+        }
+        kern<<<(unsigned)ceil_div(A->nbr, RT), nthreads, smem, st>>>(a, x, y);
+        BMSP_KERNEL_CHECK();
+        return BMSP_OK;
+    }
     if (A->spmv_path == 0) {
         SpmvArgs<T> a;
         a.bmps = A->bmps; a.bcol = A->bcol; a.values = (const T*)A->values; a.brp = A->brp; a.rvb = A->rvb;
         a.rows = A->rows; a.nbr = A->nbr; a.ntiles = (int)ceil_div(A->nbr, RT); a.cap_blk = A->cap_blk; a.cap_val = A->cap_val;
         const size_t smem = stage_bytes(a.cap_blk, a.cap_val, sizeof(T));
-        static int variant = -1;
-        if (variant < 0) { const char* e = getenv("BMSP_SPMV_VARIANT"); variant = e ? atoi(e) : 0; }
-        // default: 16 CTAs/SM (32 registers), two rows per round.  BMSP_SPMV_VARIANT=1 selects the four-rows-per-round
-        // build (40 registers, 12 CTAs/SM) for experiments; measured on P4096: 106.7 us vs 112.8 us.
         void (*kern)(SpmvArgs<T>, const X*, float*, int) = spmv_rowtile_kernel<T, X, 16, 2>;
-        if (variant == 1) kern = spmv_rowtile_kernel<T, X, 12, 4>;
+        if (spmv_variant() == 3) kern = spmv_rowtile_kernel<T, X, 12, 4>;
         static size_t configured = 0;
         if (configured < smem) {
             BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
