@@ -31,6 +31,7 @@ struct bmsp_matrix_s {
     int32_t spmv_path = -2;     // -2 not planned yet, 0 row-tiled (dense-ish blocks), 1 block-parallel (sparse blocks)
     int32_t cap_blk = 0, cap_val = 0;   // per-tile smem capacities of the row-tiled kernels
     int32_t cap_lines = 0;      // staged x lines per tile (tile plan)
+    int32_t tile_rows = 64;     // block rows per tile (64, 32 or 16)
     void* tile_rowpair = nullptr;   // [nbr+1] int2 (block_row_ptr, first value) zipped for one bulk copy per tile
     void* tile_desc = nullptr;  // [ntiles] TileDesc (spmv.cu): block / value / x-line ranges of every tile of 64 block rows
     uint32_t* tile_lines = nullptr;   // [nblk] distinct x lines (32 columns) of every tile, stored from the tile's first block index

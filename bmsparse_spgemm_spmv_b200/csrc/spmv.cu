@@ -7,13 +7,16 @@
 // per block, 2 B per value, 8 B per block row):
 //
 //   path 0 "row-tiled"  (dense-ish blocks: Poisson, block-clustered)
-//       one CTA (128 threads) per tile of 64 block rows; the tile's bitmaps / block columns / values / row
-//       pointers are bulk-copied (cp.async.bulk + mbarrier, SASS UBLKCP) into shared memory; 16 CTAs are
-//       resident per SM, each in a different phase, which is what hides the copy latency.  Two threads per
-//       block row, one per 32-bit bitmap half (4 matrix rows, 4 fp32 accumulators): each walks the blocks of
-//       its block row, ranks with popc, and consumes set bits in "rounds" whose loads are predicated (no
-//       branches) so several are in flight; x is read through the read-only path (L1/L2); y is stored as
-//       one float4 per thread.
+//       one CTA per tile of 64 (32, 16 for heavy rows) block rows.  A per-matrix tile plan lists, for every tile, the
+//       distinct 32-column lines of x its blocks touch and gives every block a 16-bit offset into the tile's staged
+//       copy of those lines.  The tile's bitmaps / x offsets / values / row pointers are bulk-copied (cp.async.bulk +
+//       mbarrier, SASS UBLKCP) into shared memory while all threads gather the x lines with coalesced 16-byte loads;
+//       12+ CTAs are resident per SM, each in a different phase, which is what hides the copy latency.  Two threads
+//       per block row, one per 32-bit bitmap half (4 matrix rows, 4 fp32 accumulators): each walks the blocks of its
+//       block row, ranks with popc, and consumes set bits two rows at a time in predicated rounds (one PTX block per
+//       row pair, no branches except the early exit); every per-value read (fp16 value, fp32 x) is a shared-memory
+//       load; y is stored as one float4 per thread.  Tiles that exceed the shared-memory capacities are read from
+//       global memory by the same threads.
 //   path 1 "block-parallel" (about one value per block: uniform random, R-MAT)
 //       one warp per work item (a block row, or a 4096-block slice of a long one); lane <-> block,
 //       coalesced 8 B + 4 B metadata loads, value offsets by a warp scan of popc, eight per-row partial
@@ -25,21 +28,7 @@
 
 namespace bmsp {
 
-constexpr int RT = 64;             // block rows per tile (path 0)
-constexpr int SPMV_THREADS = 2 * RT;   // two threads per block row: one per 32-bit bitmap half (4 matrix rows each)
 constexpr int SLICE = 4096;        // blocks per work item (path 1)
-constexpr int ROWSLOT = RT + 4;    // staged row-pointer slice, padded to a 16-byte multiple
-
-template <typename T>
-struct SpmvArgs {
-    const uint64_t* bmps; const int32_t* bcol; const T* values;
-    const int32_t* brp; const uint32_t* rvb;
-    int32_t rows, nbr, ntiles, cap_blk, cap_val;
-};
-
-__host__ __device__ inline size_t stage_bytes(int cap_blk, int cap_val, int vsize) {
-    return (size_t)(cap_blk + 4) * 8 + (size_t)(cap_blk + 4) * 4 + (size_t)(cap_val + 8) * vsize + 2 * ROWSLOT * 4 + 16 + 16;   // + x slots, added by the launcher
-}
 
 template <typename X> __device__ __forceinline__ float ld_xp(const X* p);
 template <> __device__ __forceinline__ float ld_xp<float>(const float* p) { return __ldg(p); }
@@ -91,7 +80,7 @@ __device__ __forceinline__ void half_block_row(const uint64_t* __restrict__ bm, 
     }
 }
 
-// ---- shared-memory fast path: explicit 32-bit shared addresses (no generic-pointer arithmetic) ----
+// ---- explicit 32-bit shared addresses (no generic-pointer arithmetic) ----
 __device__ __forceinline__ uint2 lds_v2(uint32_t a) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
@@ -102,196 +91,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
-__device__ __forceinline__ float lds_f32(uint32_t a) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ float lds_val(uint32_t a, __half) {
-    unsigned short u;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(a));
-    return __half2float(__ushort_as_half(u));
-}
-__device__ __forceinline__ float lds_val(uint32_t a, float) { return lds_f32(a); }
-__device__ __forceinline__ float lds_x(uint32_t a, __half h) { return lds_val(a, h); }
-__device__ __forceinline__ float lds_x(uint32_t a, float) { return lds_f32(a); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-
-// One "round" = the next set bit (ascending column) of each of the four 8-bit row masks of a bitmap half.
-// row_issue does the bit bookkeeping and issues the two loads of one row PREDICATED (no branches), so the
-// eight loads of a round are in flight together; the FMAs follow.  b is the row mask MSB-aligned, va the
-// shared address of the row's next value, xs31 = the block's x segment + 31 elements (the found bit
-// position p indexes it as xs31 - p).  SASS: FLO, BMSK, IMAD.WIDE, @P LDG, @P LDS, LOP3, @P IADD.
-template <typename T, typename X> struct RowLoad;
-template <> struct RowLoad<__half, float> {
-    float xv; unsigned short raw;
-    __device__ __forceinline__ void issue(uint32_t& b, uint32_t& va, const float* xs31) {
-        asm volatile("{\n\t.reg .pred pq;\n\t.reg .u32 pp, mm;\n\t.reg .u64 ad;\n\t"
-                     "setp.ne.u32 pq, %2, 0;\n\tbfind.u32 pp, %2;\n\tbmsk.clamp.b32 mm, pp, 1;\n\tmad.wide.s32 ad, pp, -4, %4;\n\t"
-                     "@pq ld.global.nc.f32 %0, [ad];\n\t@pq ld.shared.u16 %1, [%3];\n\t"
-                     "not.b32 mm, mm;\n\tand.b32 %2, %2, mm;\n\t@pq add.u32 %3, %3, 2;\n\t}"
-                     : "=f"(xv), "=h"(raw), "+r"(b), "+r"(va) : "l"(xs31));
-    }
-    __device__ __forceinline__ float prod_add(float acc) const { return fmaf(__half2float(__ushort_as_half(raw)), xv, acc); }
-};
-template <> struct RowLoad<__half, __half> {
-    unsigned short xr, raw;
-    __device__ __forceinline__ void issue(uint32_t& b, uint32_t& va, const __half* xs31) {
-        asm volatile("{\n\t.reg .pred pq;\n\t.reg .u32 pp, mm;\n\t.reg .u64 ad;\n\t"
-                     "setp.ne.u32 pq, %2, 0;\n\tbfind.u32 pp, %2;\n\tbmsk.clamp.b32 mm, pp, 1;\n\tmad.wide.s32 ad, pp, -2, %4;\n\t"
-                     "@pq ld.global.nc.u16 %0, [ad];\n\t@pq ld.shared.u16 %1, [%3];\n\t"
-                     "not.b32 mm, mm;\n\tand.b32 %2, %2, mm;\n\t@pq add.u32 %3, %3, 2;\n\t}"
-                     : "=h"(xr), "=h"(raw), "+r"(b), "+r"(va) : "l"(xs31));
-    }
-    __device__ __forceinline__ float prod_add(float acc) const {
-        return fmaf(__half2float(__ushort_as_half(raw)), __half2float(__ushort_as_half(xr)), acc);
-    }
-};
-template <> struct RowLoad<float, float> {
-    float xv, raw;
-    __device__ __forceinline__ void issue(uint32_t& b, uint32_t& va, const float* xs31) {
-        asm volatile("{\n\t.reg .pred pq;\n\t.reg .u32 pp, mm;\n\t.reg .u64 ad;\n\t"
-                     "setp.ne.u32 pq, %2, 0;\n\tbfind.u32 pp, %2;\n\tbmsk.clamp.b32 mm, pp, 1;\n\tmad.wide.s32 ad, pp, -4, %4;\n\t"
-                     "@pq ld.global.nc.f32 %0, [ad];\n\t@pq ld.shared.f32 %1, [%3];\n\t"
-                     "not.b32 mm, mm;\n\tand.b32 %2, %2, mm;\n\t@pq add.u32 %3, %3, 4;\n\t}"
-                     : "=f"(xv), "=f"(raw), "+r"(b), "+r"(va) : "l"(xs31));
-    }
-    __device__ __forceinline__ float prod_add(float acc) const { return fmaf(raw, xv, acc); }
-};
-template <> struct RowLoad<float, __half> {
-    unsigned short xr; float raw;
-    __device__ __forceinline__ void issue(uint32_t& b, uint32_t& va, const __half* xs31) {
-        asm volatile("{\n\t.reg .pred pq;\n\t.reg .u32 pp, mm;\n\t.reg .u64 ad;\n\t"
-                     "setp.ne.u32 pq, %2, 0;\n\tbfind.u32 pp, %2;\n\tbmsk.clamp.b32 mm, pp, 1;\n\tmad.wide.s32 ad, pp, -2, %4;\n\t"
-                     "@pq ld.global.nc.u16 %0, [ad];\n\t@pq ld.shared.f32 %1, [%3];\n\t"
-                     "not.b32 mm, mm;\n\tand.b32 %2, %2, mm;\n\t@pq add.u32 %3, %3, 4;\n\t}"
-                     : "=h"(xr), "=f"(raw), "+r"(b), "+r"(va) : "l"(xs31));
-    }
-    __device__ __forceinline__ float prod_add(float acc) const { return fmaf(raw, __half2float(__ushort_as_half(xr)), acc); }
-};
-
-// The blocks of one block row seen by the thread that owns bitmap half h (rows 4h..4h+3); bitmaps and
-// values in shared memory (32-bit shared addresses), x through the read-only path.
-template <typename T, typename X, int RPR>
-__device__ __forceinline__ void half_block_row_s(uint32_t a_bm, uint32_t a_bc, uint32_t a_val, int nb, uint32_t k, const int h,
-                                                 const X* __restrict__ x, float (&acc)[4]) {
-    const uint32_t hm = 0u - (uint32_t)h;
-    for (int i = 0; i < nb; i++) {
-        const uint2 w2 = lds_v2(a_bm);                  // .y = rows 0-3, .x = rows 4-7
-        a_bm += 8;
-        const uint32_t nhi = __popc(w2.y), nlo = __popc(w2.x);
-        const uint32_t w = h ? w2.x : w2.y;
-        const uint32_t va = a_val + (k + (nhi & hm)) * (uint32_t)sizeof(T);
-        k += nhi + nlo;
-        if (w) {
-            const X* xs31 = x + (size_t)lds_u32(a_bc) * 8 + 31;
-            uint32_t b0 = w & 0xFF000000u, b1 = (w << 8) & 0xFF000000u, b2 = (w << 16) & 0xFF000000u, b3 = w << 24;
-            uint32_t va0 = va, va1 = va0 + __popc(b0) * (uint32_t)sizeof(T), va2 = va1 + __popc(b1) * (uint32_t)sizeof(T),
-                     va3 = va2 + __popc(b2) * (uint32_t)sizeof(T);
-            if (RPR == 4) {
-                do {
-                    const bool q0 = b0 != 0, q1 = b1 != 0, q2 = b2 != 0, q3 = b3 != 0;
-                    RowLoad<T, X> l0, l1, l2, l3;
-                    l0.issue(b0, va0, xs31);
-                    l1.issue(b1, va1, xs31);
-                    l2.issue(b2, va2, xs31);
-                    l3.issue(b3, va3, xs31);
-                    if (q0) acc[0] = l0.prod_add(acc[0]);
-                    if (q1) acc[1] = l1.prod_add(acc[1]);
-                    if (q2) acc[2] = l2.prod_add(acc[2]);
-                    if (q3) acc[3] = l3.prod_add(acc[3]);
-                } while (b0 | b1 | b2 | b3);
-            } else {
-                while (b0 | b1) {
-                    const bool q0 = b0 != 0, q1 = b1 != 0;
-                    RowLoad<T, X> l0, l1;
-                    l0.issue(b0, va0, xs31);
-                    l1.issue(b1, va1, xs31);
-                    if (q0) acc[0] = l0.prod_add(acc[0]);
-                    if (q1) acc[1] = l1.prod_add(acc[1]);
-                }
-                while (b2 | b3) {
-                    const bool q2 = b2 != 0, q3 = b3 != 0;
-                    RowLoad<T, X> l2, l3;
-                    l2.issue(b2, va2, xs31);
-                    l3.issue(b3, va3, xs31);
-                    if (q2) acc[2] = l2.prod_add(acc[2]);
-                    if (q3) acc[3] = l3.prod_add(acc[3]);
-                }
-            }
-        }
-        a_bc += 4;
-    }
-}
-
-struct TileMeta { int32_t p0, p1; uint32_t v0a; int32_t staged; };
-
-// One CTA per tile, a single staging buffer: latency is hidden by the CTAs resident per SM, each in a
-// different phase (row pointers -> bulk copies in flight -> x gather in flight -> compute -> store).
-template <typename T, typename X, int MINB, int RPR>
-__global__ void __launch_bounds__(SPMV_THREADS, MINB) spmv_rowtile_kernel(SpmvArgs<T> a, const X* __restrict__ x, float* __restrict__ y, int ncols) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int VA = 16 / sizeof(T);   // values per 16 bytes
-    const int tid = threadIdx.x;
-    const uint32_t off_bc = (uint32_t)(a.cap_blk + 4) * 8, off_val = (uint32_t)(a.cap_blk + 4) * 12;
-    const uint32_t off_brp = off_val + (uint32_t)(a.cap_val + 8) * sizeof(T);
-    const uint32_t off_rvb = off_brp + ROWSLOT * 4, off_meta = off_rvb + ROWSLOT * 4, off_bar = off_meta + 16;
-    TileMeta* s_meta = reinterpret_cast<TileMeta*>(smem + off_meta);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + off_bar);
-    const uint32_t sbase = smem_u32(smem);
-
-    const int t = blockIdx.x;
-    const int r0 = t * RT, r1 = min(r0 + RT, a.nbr);
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-        const int p0 = a.brp[r0], p1 = a.brp[r1];
-        const uint32_t v0 = a.rvb[r0], v1 = a.rvb[r1];
-        TileMeta m;
-        m.p0 = p0; m.p1 = p1; m.v0a = v0 & ~(uint32_t)(VA - 1);
-        m.staged = (p1 - p0 <= a.cap_blk) && ((int64_t)v1 - v0 <= a.cap_val);
-        *s_meta = m;
-        const int p0a = p0 & ~1, p0c = p0 & ~3;
-        const uint32_t nrow = (uint32_t)(((r1 - r0 + 1) + 3) & ~3) * 4;
-        uint32_t n8 = 0, n4 = 0, nv = 0;
-        if (m.staged) {
-            n8 = (uint32_t)((p1 - p0a + 1) & ~1) * 8;
-            n4 = (uint32_t)((p1 - p0c + 3) & ~3) * 4;
-            nv = (uint32_t)((v1 - m.v0a + VA - 1) & ~(uint32_t)(VA - 1)) * sizeof(T);
-        }
-        mbar_arrive_expect_tx(bar, n8 + n4 + nv + 2 * nrow);
-        bulk_g2s(smem + off_brp, a.brp + r0, nrow, bar);
-        bulk_g2s(smem + off_rvb, a.rvb + r0, nrow, bar);
-        if (n8) bulk_g2s(smem, a.bmps + p0a, n8, bar);
-        if (n4) bulk_g2s(smem + off_bc, a.bcol + p0c, n4, bar);
-        if (nv) bulk_g2s(smem + off_val, a.values + m.v0a, nv, bar);
-    }
-    __syncthreads();                 // barrier initialised and armed before anyone polls it
-    mbar_wait(bar, 0);
-
-    const TileMeta m = *s_meta;
-    const int lbr = tid >> 1, h = tid & 1;
-    const int64_t row = ((int64_t)(r0 + lbr)) * 8 + h * 4;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (m.staged) {
-        if (row >= a.rows) return;
-        const uint32_t pb = lds_u32(sbase + off_brp + 4u * lbr), pe = lds_u32(sbase + off_brp + 4u * lbr + 4u);
-        const uint32_t k = lds_u32(sbase + off_rvb + 4u * lbr) - m.v0a;
-        const uint32_t rel = pb - (uint32_t)m.p0;
-        half_block_row_s<T, X, RPR>(sbase + ((uint32_t)(m.p0 & 1) + rel) * 8u, sbase + off_bc + ((uint32_t)(m.p0 & 3) + rel) * 4u, sbase + off_val,
-                               (int)(pe - pb), k, h, x, acc);
-    } else {
-        if (row >= a.rows) return;
-        const int32_t* s_brp = reinterpret_cast<const int32_t*>(smem + off_brp);
-        const uint32_t* s_rvb = reinterpret_cast<const uint32_t*>(smem + off_rvb);
-        half_block_row<T, X>(a.bmps, a.bcol, a.values + m.v0a, s_brp[lbr], s_brp[lbr + 1], s_rvb[lbr] - m.v0a, h, x, acc);
-    }
-    if (row + 4 <= a.rows) *reinterpret_cast<float4*>(y + row) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    else for (int q = 0; q < 4; q++) if (row + q < a.rows) y[row + q] = acc[q];
-}
-
 
 // ===================================================================================== path 0, tile plan
 // Built once per matrix (plan_spmv): for every tile of RT block rows, the sorted distinct x "lines" (32 columns
@@ -299,7 +98,7 @@ __global__ void __launch_bounds__(SPMV_THREADS, MINB) spmv_rowtile_kernel(SpmvAr
 // inside the tile's staged copy of those lines.  The kernel then never reads block_col: it streams bitmaps
 // (8 B), x offsets (2 B) and values per block, gathers each distinct x line ONCE per tile with coalesced
 // 16-byte loads (8 threads per line) and serves every per-value x read from shared memory.  Staged lines
-// have a pitch of 34 elements: when the 16 block rows of a warp read the same column of consecutive block
+// have a pitch of 33 elements: when the 16 block rows of a warp read the same column of consecutive block
 // columns (stencils, bands) the 16 addresses fall into 16 different banks.
 constexpr int XL_STRIDE = 33;      // staged x line pitch, elements (32 + 1 skew)
 constexpr int PLAN_MAXB = 2048;    // blocks per tile the planner sorts in shared memory
@@ -308,14 +107,14 @@ constexpr int XL_MAX = 1900;       // distinct lines per tile (16-bit element of
 struct __align__(16) TileDesc { int32_t p0, nb; uint32_t v0; int32_t nv, nl, flags, pad0, pad1; };   // 32 bytes
 
 __global__ void __launch_bounds__(256) tile_plan_kernel(const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
-                                                        const uint32_t* __restrict__ rvb, int nbr, int ncols, TileDesc* __restrict__ desc,
+                                                        const uint32_t* __restrict__ rvb, int nbr, int ncols, int rt, TileDesc* __restrict__ desc,
                                                         uint32_t* __restrict__ lines, uint16_t* __restrict__ xoff,
                                                         unsigned long long* __restrict__ stats) {
     __shared__ uint32_t s_key[PLAN_MAXB];
     __shared__ uint32_t s_uniq[PLAN_MAXB];
     __shared__ uint32_t s_w[9];
     const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int r0 = t * RT, r1 = min(r0 + RT, nbr);
+    const int r0 = t * rt, r1 = min(r0 + rt, nbr);
     const int p0 = brp[r0], nb = brp[r1] - p0;
     const uint32_t v0 = rvb[r0], v1 = rvb[r1];
     TileDesc d;
@@ -389,12 +188,12 @@ __global__ void __launch_bounds__(256) tile_plan_kernel(const int32_t* __restric
 
 // shared-memory carve-up of spmv_tile_kernel (cap_blk and cap_val are multiples of 8); computed on the host
 struct TileSmem { uint32_t xo, val, row, xs, bar, total; };
-inline TileSmem tile_smem(int cap_blk, int cap_val, int cap_lines, int vsize, int xsize) {
+inline TileSmem tile_smem(int rt, int cap_blk, int cap_val, int cap_lines, int vsize, int xsize) {
     TileSmem s;
     s.xo = (uint32_t)(cap_blk + 2) * 8;
     s.val = s.xo + (uint32_t)(cap_blk + 16) * 2;
     s.row = s.val + (uint32_t)(cap_val + 16) * vsize;
-    s.xs = s.row + (RT + 2) * 8;
+    s.xs = s.row + (uint32_t)(rt + 2) * 8;
     s.bar = (s.xs + (uint32_t)cap_lines * XL_STRIDE * xsize + 15u) & ~15u;
     s.total = s.bar + 16;
     return s;
@@ -418,11 +217,6 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
     return v;
 }
-template <int BYTES>
-__device__ __forceinline__ void cp_async_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(dst), "l"(src), "n"(BYTES), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // Two 8-bit row masks b0, b1 of one bitmap half (left in place: row r of the half occupies bits 31-8r..24-8r)
 // advance together: every round takes the highest set bit p of each mask, multiplies the row's next value
@@ -543,18 +337,19 @@ template <> __device__ __forceinline__ void sts_x<__half>(uint32_t a, __half v) 
 }
 template <typename X> struct alignas(4 * sizeof(X)) XQuad { X e[4]; };
 
-// One CTA per tile of RT block rows, TPR threads per block row (1: a thread owns all 8 matrix rows of its block
+// One CTA per tile of RTT block rows, TPR threads per block row (1: a thread owns all 8 matrix rows of its block
 // row; 2: one thread per 32-bit bitmap half).  Every thread reads the 32-byte tile descriptor; thread 0 arms the
 // mbarrier and issues the bulk copies (row pointers, bitmaps, x offsets, values) while all threads gather the
 // tile's distinct x lines (coalesced 16-byte loads, stored at a 33-element pitch); latency is hidden by the CTAs
 // resident per SM, each in a different phase.
-template <typename T, typename X, int TPR, int MINB>
-__global__ void __launch_bounds__(RT * TPR, MINB) spmv_tile_kernel(const TileArgs<T> a, const X* __restrict__ x, float* __restrict__ y) {
+template <typename T, typename X, int RTT, int TPR, int MINB>
+__global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileArgs<T> a, const X* __restrict__ x, float* __restrict__ y) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int VA = 16 / sizeof(T);   // values per 16 bytes
-    constexpr int NT = RT * TPR;
+    constexpr int NT = RTT * TPR;
     constexpr int LPI = NT / 8;          // x lines per gather step (8 threads per line)
     constexpr int GB = TPR == 1 ? 8 : 4; // gather steps in flight
+    static_assert(NT >= 8 && NT % 8 == 0, "8 threads per x line");
     constexpr uint32_t SX = sizeof(X);
     const int tid = threadIdx.x, t = blockIdx.x;
     const uint32_t sbase = smem_u32(smem);
@@ -566,7 +361,7 @@ __global__ void __launch_bounds__(RT * TPR, MINB) spmv_tile_kernel(const TileArg
     const int p0 = d0.x, nb = d0.y, nv = d0.w, nl = d1.x;
     const uint32_t v0 = (uint32_t)d0.z, v0a = v0 & ~(uint32_t)(VA - 1);
     const bool staged = (d1.y & 1) && nb <= a.cap_blk && nv <= a.cap_val && nl <= a.cap_lines;
-    const int r0 = t * RT, nrow = min(RT, a.nbr - r0);
+    const int r0 = t * RTT, nrow = min(RTT, a.nbr - r0);
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -749,7 +544,13 @@ static int spmv_variant() {
 // path 0 plan: tile descriptors, x lines and per-block x offsets; shared-memory capacities from the tile maxima
 // when they fit the per-CTA budget, else from the averages (larger tiles are then read from global memory).
 static int plan_tiles(bmsp_matrix_s* m, cudaStream_t st) {
-    const int ntiles = (int)ceil_div(m->nbr, RT);
+    const int vsize = m->dtype == BMSP_F16 ? 2 : 4;
+    // tile height: 64 block rows unless an average tile (bitmaps, x offsets, values, ~x lines) would not fit ~20 KB
+    int rt = 64;
+    const double row_bytes = ((double)m->nblk * (8 + 2 + 16) + (double)m->nnz * vsize) / m->nbr + 8;
+    while (rt > 16 && row_bytes * rt > 20.0 * 1024) rt >>= 1;
+    m->tile_rows = rt;
+    const int ntiles = (int)ceil_div(m->nbr, rt);
     unsigned long long* stats = nullptr;
     BMSP_TRY(dev_alloc((void**)&m->tile_desc, sizeof(TileDesc) * (size_t)ntiles, st));
     BMSP_TRY(dev_alloc_t(&m->tile_lines, (size_t)m->nblk + 8, st));
@@ -759,21 +560,22 @@ static int plan_tiles(bmsp_matrix_s* m, cudaStream_t st) {
     BMSP_KERNEL_CHECK();
     BMSP_TRY(dev_alloc_t(&stats, 8, st));
     BMSP_CUDA(cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), st));
-    tile_plan_kernel<<<ntiles, 256, 0, st>>>(m->brp, m->bcol, m->rvb, m->nbr, m->cols, (TileDesc*)m->tile_desc, m->tile_lines, m->tile_xoff, stats);
+    tile_plan_kernel<<<ntiles, 256, 0, st>>>(m->brp, m->bcol, m->rvb, m->nbr, m->cols, rt, (TileDesc*)m->tile_desc, m->tile_lines, m->tile_xoff, stats);
     BMSP_KERNEL_CHECK();
     unsigned long long h[8];
     BMSP_CUDA(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, st));
     BMSP_CUDA(cudaStreamSynchronize(st));
     dev_free(stats, st);
-    const int vsize = m->dtype == BMSP_F16 ? 2 : 4;
+    // capacities: the tile maxima when they fit the per-CTA budget, else 1.25 x the averages (larger tiles are then
+    // read from global memory by the kernel)
     auto up8 = [](long long v) { return (int)((v + 7) & ~7ll); };
     int cb = up8((long long)h[0]), cv = up8((long long)h[1]), cl = (int)h[2];
     const size_t budget = 40 * 1024;
-    if (tile_smem(cb, cv, cl, vsize, 4).total > budget) {
+    if (tile_smem(rt, cb, cv, cl, vsize, 4).total > budget) {
         const double ab = (double)m->nblk / ntiles, av = (double)m->nnz / ntiles, al = (double)h[3] / ntiles;
         cb = std::min(cb, up8((long long)(ab * 1.25) + 16)); cv = std::min(cv, up8((long long)(av * 1.25) + 64));
         cl = std::min(cl, (int)(al * 1.25) + 4);
-        while (tile_smem(cb, cv, cl, vsize, 4).total > budget && (cb > 64 || cv > 256 || cl > 16)) {
+        while (tile_smem(rt, cb, cv, cl, vsize, 4).total > budget && (cb > 64 || cv > 256 || cl > 16)) {
             cb = std::max(64, up8(cb * 3 / 4)); cv = std::max(256, up8(cv * 3 / 4)); cl = std::max(16, cl * 3 / 4);
         }
     }
@@ -785,20 +587,7 @@ int plan_spmv(bmsp_matrix_s* m, cudaStream_t st) {
     if (m->transposed || m->nbr == 0) { m->spmv_path = -1; return BMSP_OK; }
     const double per_blk = m->nblk ? (double)m->nnz / (double)m->nblk : 0.0;
     m->spmv_path = per_blk >= 2.5 ? 0 : 1;
-    if (m->spmv_path == 0 && spmv_variant() < 2) return plan_tiles(m, st);
-    if (m->spmv_path == 0) {
-        const int vsize = m->dtype == BMSP_F16 ? 2 : 4;
-        double ab = (double)m->nblk / m->nbr * RT, av = (double)m->nnz / m->nbr * RT;
-        int cb = (int)(ab * 1.125) + 16, cv = (int)(av * 1.125) + 64;
-        cb = (cb + 3) & ~3; cv = (cv + 7) & ~7;
-        const size_t budget = 48 * 1024;
-        while (stage_bytes(cb, cv, vsize) > budget && (cb > 64 || cv > 256)) {
-            cb = max(64, ((cb * 3 / 4) + 3) & ~3);
-            cv = max(256, ((cv * 3 / 4) + 7) & ~7);
-        }
-        m->cap_blk = cb; m->cap_val = cv;
-        return BMSP_OK;
-    }
+    if (m->spmv_path == 0) return plan_tiles(m, st);
     uint32_t* cnt = nullptr;
     BMSP_TRY(dev_alloc_t(&cnt, (size_t)m->nbr + 1, st));
     work_count_kernel<<<(unsigned)ceil_div(m->nbr, 256), 256, 0, st>>>(m->brp, m->nbr, cnt);
@@ -819,18 +608,22 @@ int plan_spmv(bmsp_matrix_s* m, cudaStream_t st) {
 
 template <typename T, typename X>
 static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st) {
-    if (A->spmv_path == 0 && spmv_variant() < 2) {
+    if (A->spmv_path == 0) {
         TileArgs<T> a;
         a.bmps = A->bmps; a.bcol = A->bcol; a.values = (const T*)A->values; a.rowpair = (const int2*)A->tile_rowpair;
         a.desc = (const TileDesc*)A->tile_desc; a.lines = A->tile_lines; a.xoff = A->tile_xoff;
         a.rows = A->rows; a.nbr = A->nbr; a.cols = A->cols; a.cap_blk = A->cap_blk; a.cap_val = A->cap_val; a.cap_lines = A->cap_lines;
-        a.so = tile_smem(a.cap_blk, a.cap_val, a.cap_lines, sizeof(T), sizeof(X));
+        const int rt = A->tile_rows;
+        a.so = tile_smem(rt, a.cap_blk, a.cap_val, a.cap_lines, sizeof(T), sizeof(X));
         const size_t smem = a.so.total;
-        // default: one thread per bitmap half (128-thread CTAs); BMSP_SPMV_VARIANT=1: one thread per block row (64-thread CTAs).
+        // default: one thread per bitmap half; BMSP_SPMV_VARIANT=1: one thread per block row (64-row tiles only).
         // Measured on P4096: 92.7 us vs 103.5 us (fewer instructions, but too few warps to hide the staging latency).
-        void (*kern)(TileArgs<T>, const X*, float*) = spmv_tile_kernel<T, X, 2, 12>;
-        int nthreads = 2 * RT;
-        if (spmv_variant() == 1) { kern = spmv_tile_kernel<T, X, 1, 14>; nthreads = RT; }
+        void (*kern)(TileArgs<T>, const X*, float*) = spmv_tile_kernel<T, X, 64, 2, 12>;
+        int nthreads = 2 * rt;
+        if (rt == 32) kern = spmv_tile_kernel<T, X, 32, 2, 24>;
+        else if (rt == 16) kern = spmv_tile_kernel<T, X, 16, 2, 32>;
+        else if (spmv_variant() == 1) { kern = spmv_tile_kernel<T, X, 64, 1, 14>; nthreads = rt; }
+        else if (spmv_variant() == 3) kern = spmv_tile_kernel<T, X, 64, 2, 14>;
         static size_t configured = 0;
         static void* configured_for = nullptr;
         if (configured < smem || configured_for != (void*)kern) {
@@ -838,25 +631,7 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st) 
             BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             configured = smem; configured_for = (void*)kern;
         }
-        kern<<<(unsigned)ceil_div(A->nbr, RT), nthreads, smem, st>>>(a, x, y);
-        BMSP_KERNEL_CHECK();
-        return BMSP_OK;
-    }
-    if (A->spmv_path == 0) {
-        SpmvArgs<T> a;
-        a.bmps = A->bmps; a.bcol = A->bcol; a.values = (const T*)A->values; a.brp = A->brp; a.rvb = A->rvb;
-        a.rows = A->rows; a.nbr = A->nbr; a.ntiles = (int)ceil_div(A->nbr, RT); a.cap_blk = A->cap_blk; a.cap_val = A->cap_val;
-        const size_t smem = stage_bytes(a.cap_blk, a.cap_val, sizeof(T));
-        void (*kern)(SpmvArgs<T>, const X*, float*, int) = spmv_rowtile_kernel<T, X, 16, 2>;
-        if (spmv_variant() == 3) kern = spmv_rowtile_kernel<T, X, 12, 4>;
-        static size_t configured = 0;
-        if (configured < smem) {
-            BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            configured = smem;
-        }
-        const int grid = a.ntiles;
-        kern<<<grid, SPMV_THREADS, smem, st>>>(a, x, y, A->cols);
+        kern<<<(unsigned)ceil_div(A->nbr, rt), nthreads, smem, st>>>(a, x, y);
         BMSP_KERNEL_CHECK();
         return BMSP_OK;
     }
