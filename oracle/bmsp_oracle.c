@@ -15,7 +15,7 @@
  *   (ii)  the reference's own cusp host CSR kernels compiled from the reference tree
  *         into oracle/_ref/ (see oracle/Makefile), and
  *   (iii) outputs of the reference's bmSparse CUDA binaries run on the B200 box
- *         (tests/golden/ref_*.json, generated by oracle/run_ref_on_gpu.sh).
+ *         (tests/golden/ref_cuda_golden.json, written by tests/test_gpu_reference_cuda.py on the GPU box).
  *
  * Build: make -C oracle   (gcc -O2 -fopenmp -shared)
  */
