@@ -287,17 +287,15 @@ def main():
         kern_ms = ev0.elapsed_time(ev1) / K
 
     # ---- end to end through the public API with HOST buffers: H2D x, SpMV, D2H y inside the timed region
-    xp = torch.from_numpy(x_host).pin_memory()
-    yp = torch.empty(nr, dtype=torch.float32).pin_memory()
-    xd = torch.empty(nc if world == 1 else A.num_cols, dtype=torch.float32, device=dev)
-    yd = torch.empty(nr, dtype=torch.float32, device=dev)
+    ncols_local = nc if world == 1 else A.num_cols
+    xp = torch.zeros(ncols_local, dtype=torch.float32).pin_memory()
     xoff = 0 if world == 1 else sharded.own_lo - sharded.ext_lo
-    Ke = max(3, min(K, 20))
+    xp[xoff:xoff + nr].copy_(torch.from_numpy(x_host))
+    yp = torch.empty(nr, dtype=torch.float32).pin_memory()
+    Ke = max(3, min(K, 50))
 
     def e2e_step():
-        xd[xoff:xoff + nr].copy_(xp, non_blocking=True)
-        B.bmSparse_SpMV(A, xd, yd)
-        yp.copy_(yd, non_blocking=True)
+        B.bmSparse_SpMV_host(A, xp, yp)               # H2D of x, the product, D2H of y: pipelined inside the library
         torch.cuda.current_stream().synchronize()     # the caller needs y on the host before the next step
 
     for _ in range(3):
@@ -328,9 +326,9 @@ def main():
         "roofline": {"bound": "hbm", "achieved": nbytes / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": nbytes / (kern_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": nbytes / (kern_ms * 1e-3) / 1e9 / 8000.0,
-                     "kernel": "spmv_rowtile_kernel<__half,float>", "kernel_ms": kern_ms},
-        "e2e": {"value": total_bytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nr * 4, "d2h_bytes_per_step": nr * 4,
-                "ms_per_step": e2e_s * 1e3, "note": "matrix resident in HBM (as in the reference's timed region); x from pinned host memory, y back to pinned host memory every step"},
+                     "kernel": "spmv_tile_kernel<__half,float,64,2,12>", "kernel_ms": kern_ms},
+        "e2e": {"value": total_bytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": ncols_local * 4, "d2h_bytes_per_step": nr * 4,
+                "ms_per_step": e2e_s * 1e3, "note": "bmsp_spmv_host: matrix resident in HBM (as in the reference's timed region); every step x comes from pinned host memory and y goes back to pinned host memory, chunked so that H2D, the row-range launches and D2H overlap (PCIe-bound)"},
         "gpu_launches": K * launches_per_step,
         "clocks": clocks,
         "convert_ms": conv_ms,

@@ -47,7 +47,7 @@ class SpgemmOpts(C.Structure):
 # every symbol include/bmsparse_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["bmsp_abi_version", "bmsp_last_error", "bmsp_device_info", "bmsp_create_from_csr", "bmsp_create_from_coo",
            "bmsp_create_from_mtx", "bmsp_create_from_arrays", "bmsp_destroy", "bmsp_get", "bmsp_download",
-           "bmsp_to_coo", "bmsp_compare", "bmsp_spmv", "bmsp_spmv_bytes", "bmsp_spgemm", "bmsp_block_transpose",
+           "bmsp_to_coo", "bmsp_compare", "bmsp_spmv", "bmsp_spmv_host", "bmsp_spmv_bytes", "bmsp_spgemm", "bmsp_block_transpose",
            "bmsp_partition_block_rows", "bmsp_slice_block_rows", "bmsp_debug_pair_bitmap"]
 
 _lib = None

@@ -41,6 +41,7 @@ struct bmsp_matrix_s {
     float* split_partial = nullptr;
     int32_t* split_rows = nullptr;
     int32_t max_row_blocks = 0;
+    void* host_pipe = nullptr;  // HostPipe (spmv.cu): streams, events and staging buffers of bmsp_spmv_host
 };
 
 namespace bmsp {
@@ -76,6 +77,7 @@ int exclusive_scan_u64(const uint64_t* in, uint64_t* out, int64_t n, cudaStream_
 // derive brp/bcol/rvb/kmask from keys/bmps/offsets (matrix.cu)
 int derive_compact(bmsp_matrix_s* m, cudaStream_t st);
 int plan_spmv(bmsp_matrix_s* m, cudaStream_t st);
+void spmv_host_release(bmsp_matrix_s* m);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

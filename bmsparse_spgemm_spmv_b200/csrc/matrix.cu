@@ -251,6 +251,7 @@ int bmsp_create_from_arrays(int32_t rows, int32_t cols, int64_t block_num, int64
 int bmsp_destroy(bmsp_matrix_t m) {
     if (!m) return BMSP_OK;
     cudaStream_t st = 0;
+    spmv_host_release(m);
     dev_free(m->keys, st); dev_free(m->bmps, st); dev_free(m->offsets, st); dev_free(m->values, st);
     dev_free(m->brp, st); dev_free(m->bcol, st); dev_free(m->rvb, st); dev_free(m->kmask, st);
     dev_free(m->work, st); dev_free(m->split_partial, st); dev_free(m->split_rows, st); dev_free(m->pmeta, st);

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include <cstdlib>
 #include <algorithm>
+#include <vector>
 
 namespace bmsp {
 
@@ -104,7 +105,7 @@ constexpr int XL_STRIDE = 33;      // staged x line pitch, elements (32 + 1 skew
 constexpr int PLAN_MAXB = 2048;    // blocks per tile the planner sorts in shared memory
 constexpr int XL_MAX = 1900;       // distinct lines per tile (16-bit element offsets)
 
-struct __align__(16) TileDesc { int32_t p0, nb; uint32_t v0; int32_t nv, nl, flags, pad0, pad1; };   // 32 bytes
+struct __align__(16) TileDesc { int32_t p0, nb; uint32_t v0; int32_t nv, nl, flags, lmin, lmax; };   // 32 bytes; [lmin, lmax] = x lines touched
 
 __global__ void __launch_bounds__(256) tile_plan_kernel(const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
                                                         const uint32_t* __restrict__ rvb, int nbr, int ncols, int rt, TileDesc* __restrict__ desc,
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256) tile_plan_kernel(const int32_t* __restric
     const int p0 = brp[r0], nb = brp[r1] - p0;
     const uint32_t v0 = rvb[r0], v1 = rvb[r1];
     TileDesc d;
-    d.p0 = p0; d.nb = nb; d.v0 = v0; d.nv = (int32_t)(v1 - v0); d.nl = 0; d.flags = 0; d.pad0 = d.pad1 = 0;
+    d.p0 = p0; d.nb = nb; d.v0 = v0; d.nv = (int32_t)(v1 - v0); d.nl = 0; d.flags = 0; d.lmin = 0; d.lmax = nb > 0 ? 0x7FFFFFFF : -1;
     if (nb > PLAN_MAXB) {          // too many blocks to plan: the kernel reads this tile straight from global memory
         if (tid == 0) { desc[t] = d; atomicAdd(stats + 4, 1ull); }
         return;
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(256) tile_plan_kernel(const int32_t* __restric
         }
     if (tid == 0) {
         // flags: bit 0 = planned (x offsets valid), bit 1 = the last line reaches past the last column (guarded gather)
+        if (nb > 0) { d.lmin = (int32_t)s_uniq[0]; d.lmax = (int32_t)s_uniq[nl - 1]; }
         d.nl = nl; d.flags = (ok ? 1 : 0) | ((nl > 0 && (uint64_t)s_uniq[nl - 1] * 32u + 32u > (uint64_t)ncols) ? 2 : 0);
         desc[t] = d;
         atomicMax(stats + 0, (unsigned long long)nb);
@@ -204,6 +206,7 @@ struct TileArgs {
     const uint64_t* bmps; const int32_t* bcol; const T* values; const int2* rowpair;   // rowpair[r] = (block_row_ptr[r], first value of row r)
     const TileDesc* desc; const uint32_t* lines; const uint16_t* xoff;
     int32_t rows, nbr, cols, cap_blk, cap_val, cap_lines;
+    int32_t tile0;       // first tile of this launch (row-range launches of the host-buffer pipeline)
     TileSmem so;
 };
 
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileAr
     constexpr int GB = TPR == 1 ? 8 : 4; // gather steps in flight
     static_assert(NT >= 8 && NT % 8 == 0, "8 threads per x line");
     constexpr uint32_t SX = sizeof(X);
-    const int tid = threadIdx.x, t = blockIdx.x;
+    const int tid = threadIdx.x, t = blockIdx.x + a.tile0;
     const uint32_t sbase = smem_u32(smem);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + a.so.bar);
 
@@ -606,10 +609,12 @@ int plan_spmv(bmsp_matrix_s* m, cudaStream_t st) {
     return BMSP_OK;
 }
 
+// tile0 / ntiles: path 0 only -- launch the tiles [tile0, tile0 + ntiles) (ntiles < 0: all of them)
 template <typename T, typename X>
-static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st) {
+static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, int tile0 = 0, int ntiles = -1) {
     if (A->spmv_path == 0) {
         TileArgs<T> a;
+        a.tile0 = tile0;
         a.bmps = A->bmps; a.bcol = A->bcol; a.values = (const T*)A->values; a.rowpair = (const int2*)A->tile_rowpair;
         a.desc = (const TileDesc*)A->tile_desc; a.lines = A->tile_lines; a.xoff = A->tile_xoff;
         a.rows = A->rows; a.nbr = A->nbr; a.cols = A->cols; a.cap_blk = A->cap_blk; a.cap_val = A->cap_val; a.cap_lines = A->cap_lines;
@@ -631,7 +636,9 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st) 
             BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             configured = smem; configured_for = (void*)kern;
         }
-        kern<<<(unsigned)ceil_div(A->nbr, rt), nthreads, smem, st>>>(a, x, y);
+        const int grid = ntiles < 0 ? (int)ceil_div(A->nbr, rt) : ntiles;
+        if (grid <= 0) return BMSP_OK;
+        kern<<<(unsigned)grid, nthreads, smem, st>>>(a, x, y);
         BMSP_KERNEL_CHECK();
         return BMSP_OK;
     }
@@ -646,9 +653,173 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st) 
     return BMSP_OK;
 }
 
+// ------------------------------------------------------------------------------------ host-buffer pipeline
+// y_host = A x_host with both vectors in (pinned) host memory: the block rows are cut into chunks of whole tiles;
+// chunk c needs the columns [0, x_need[c]) of x (running maximum of the tile plan's line ranges -- for a banded matrix
+// the frontier advances with the rows, for a scattered one the first chunk needs everything and only the y copies
+// overlap).  Three streams: s_in feeds x slices (H2D), the caller's stream runs the row-range launches, s_out drains
+// y slices (D2H); PCIe is full duplex, so the step costs max(x, y) bytes over the link instead of their sum.
+struct HostPipe {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr;
+    std::vector<cudaEvent_t> ev_x, ev_k;
+    void* x_dev = nullptr;
+    float* y_dev = nullptr;
+    // the whole pipeline of one (x_host, y_host) pair captured as a CUDA graph: one launch instead of ~7 API calls per chunk
+    cudaStream_t s_cap = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    const void* g_x = nullptr; const void* g_y = nullptr; int32_t g_xdt = -1;      // what gexec was captured for
+    const void* seen_x = nullptr; const void* seen_y = nullptr; int32_t seen_xdt = -1;   // the previous call's buffers
+    int nchunks = 0;
+    std::vector<int> tile_lo;        // [nchunks+1] first tile of every chunk (path 0); {0, 0} for path 1
+    std::vector<int64_t> x_need;     // [nchunks]  columns that must be resident before the chunk runs
+};
+
+static int host_pipe_get(bmsp_matrix_s* A, cudaStream_t st, HostPipe** out) {
+    if (A->host_pipe) { *out = (HostPipe*)A->host_pipe; return BMSP_OK; }
+    HostPipe* hp = new HostPipe();
+    A->host_pipe = hp;        // released by spmv_host_release (bmsp_destroy) whatever happens below
+    BMSP_CUDA(cudaStreamCreateWithFlags(&hp->s_in, cudaStreamNonBlocking));
+    BMSP_CUDA(cudaStreamCreateWithFlags(&hp->s_out, cudaStreamNonBlocking));
+    BMSP_CUDA(cudaEventCreateWithFlags(&hp->ev_start, cudaEventDisableTiming));
+    BMSP_CUDA(cudaEventCreateWithFlags(&hp->ev_done, cudaEventDisableTiming));
+    BMSP_TRY(dev_alloc(&hp->x_dev, (size_t)A->cols * 4 + 256, st));
+    BMSP_TRY(dev_alloc_t(&hp->y_dev, (size_t)A->rows + 64, st));
+    BMSP_CUDA(cudaStreamCreateWithFlags(&hp->s_cap, cudaStreamNonBlocking));
+    int want = 32;
+    if (const char* e = getenv("BMSP_HOST_CHUNKS")) want = std::max(1, atoi(e));
+    if (A->spmv_path == 0 && (int64_t)A->rows * 4 >= (1 << 20)) {
+        const int rt = A->tile_rows, ntiles = (int)ceil_div(A->nbr, rt);
+        std::vector<TileDesc> desc((size_t)ntiles);
+        BMSP_CUDA(cudaMemcpyAsync(desc.data(), A->tile_desc, sizeof(TileDesc) * (size_t)ntiles, cudaMemcpyDeviceToHost, st));
+        BMSP_CUDA(cudaStreamSynchronize(st));
+        const int nch = std::min(want, ntiles), per = (int)ceil_div(ntiles, nch);
+        int64_t need = 0;
+        for (int t0 = 0; t0 < ntiles; t0 += per) {
+            const int t1 = std::min(ntiles, t0 + per);
+            for (int t = t0; t < t1; t++)
+                if (desc[t].nb > 0) need = std::max(need, std::min<int64_t>(A->cols, ((int64_t)desc[t].lmax + 1) * 32));
+            hp->tile_lo.push_back(t0);
+            hp->x_need.push_back(need);
+        }
+        hp->tile_lo.push_back(ntiles);
+    } else {
+        hp->tile_lo = {0, 0};
+        hp->x_need = {(int64_t)A->cols};
+    }
+    hp->nchunks = (int)hp->x_need.size();
+    hp->ev_x.resize(hp->nchunks); hp->ev_k.resize(hp->nchunks);
+    for (auto& e : hp->ev_x) BMSP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : hp->ev_k) BMSP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *out = hp;
+    return BMSP_OK;
+}
+
+void spmv_host_release(bmsp_matrix_s* m) {
+    HostPipe* hp = (HostPipe*)m->host_pipe;
+    if (!hp) return;
+    if (hp->s_in) { cudaStreamSynchronize(hp->s_in); cudaStreamDestroy(hp->s_in); }
+    if (hp->s_out) { cudaStreamSynchronize(hp->s_out); cudaStreamDestroy(hp->s_out); }
+    if (hp->s_cap) { cudaStreamSynchronize(hp->s_cap); cudaStreamDestroy(hp->s_cap); }
+    if (hp->gexec) cudaGraphExecDestroy(hp->gexec);
+    if (hp->ev_start) cudaEventDestroy(hp->ev_start);
+    if (hp->ev_done) cudaEventDestroy(hp->ev_done);
+    for (auto e : hp->ev_x) if (e) cudaEventDestroy(e);
+    for (auto e : hp->ev_k) if (e) cudaEventDestroy(e);
+    dev_free(hp->x_dev, 0); dev_free(hp->y_dev, 0);
+    delete hp;
+    m->host_pipe = nullptr;
+}
+
+template <typename T>
+static int spmv_host_run(bmsp_matrix_s* A, HostPipe* hp, const void* x_host, int32_t x_dtype, float* y_host, cudaStream_t st) {
+    const size_t xs = x_dtype == BMSP_F16 ? 2 : 4;
+    BMSP_CUDA(cudaEventRecord(hp->ev_start, st));         // earlier work on st (and the previous call) is done with x_dev / y_dev
+    BMSP_CUDA(cudaStreamWaitEvent(hp->s_in, hp->ev_start, 0));
+    BMSP_CUDA(cudaStreamWaitEvent(hp->s_out, hp->ev_start, 0));
+    int64_t sent = 0;
+    const int64_t rows_per_tile = (int64_t)A->tile_rows * 8;
+    cudaEvent_t last_x = nullptr;
+    for (int c = 0; c < hp->nchunks; c++) {
+        const int64_t need = hp->x_need[c];
+        if (need > sent) {
+            BMSP_CUDA(cudaMemcpyAsync((char*)hp->x_dev + sent * xs, (const char*)x_host + sent * xs, (size_t)(need - sent) * xs,
+                                      cudaMemcpyHostToDevice, hp->s_in));
+            BMSP_CUDA(cudaEventRecord(hp->ev_x[c], hp->s_in));
+            BMSP_CUDA(cudaStreamWaitEvent(st, hp->ev_x[c], 0));
+            sent = need; last_x = hp->ev_x[c];
+        }
+        int64_t row0 = 0, row1 = A->rows;
+        if (A->spmv_path == 0) {
+            const int t0 = hp->tile_lo[c], t1 = hp->tile_lo[c + 1];
+            row0 = std::min<int64_t>(A->rows, t0 * rows_per_tile); row1 = std::min<int64_t>(A->rows, t1 * rows_per_tile);
+            if (x_dtype == BMSP_F32) BMSP_TRY((launch_spmv<T, float>(A, (const float*)hp->x_dev, hp->y_dev, st, t0, t1 - t0)));
+            else BMSP_TRY((launch_spmv<T, __half>(A, (const __half*)hp->x_dev, hp->y_dev, st, t0, t1 - t0)));
+        } else {
+            if (x_dtype == BMSP_F32) BMSP_TRY((launch_spmv<T, float>(A, (const float*)hp->x_dev, hp->y_dev, st)));
+            else BMSP_TRY((launch_spmv<T, __half>(A, (const __half*)hp->x_dev, hp->y_dev, st)));
+        }
+        if (row1 > row0) {
+            BMSP_CUDA(cudaEventRecord(hp->ev_k[c], st));
+            BMSP_CUDA(cudaStreamWaitEvent(hp->s_out, hp->ev_k[c], 0));
+            BMSP_CUDA(cudaMemcpyAsync(y_host + row0, hp->y_dev + row0, (size_t)(row1 - row0) * 4, cudaMemcpyDeviceToHost, hp->s_out));
+        }
+    }
+    BMSP_CUDA(cudaEventRecord(hp->ev_done, hp->s_out));
+    BMSP_CUDA(cudaStreamWaitEvent(st, hp->ev_done, 0));   // the caller synchronises `st` as for bmsp_spmv
+    (void)last_x;                                          // s_in is already joined: st waited on its last event above
+    return BMSP_OK;
+}
+
+// Second call with the same pinned buffers: capture the pipeline once (origin stream s_cap, forks into s_in / s_out, all
+// joined before the capture ends) and replay it with one cudaGraphLaunch on the caller's stream from then on.
+template <typename T>
+static int spmv_host_graph(bmsp_matrix_s* A, HostPipe* hp, const void* x_host, int32_t x_dtype, float* y_host, cudaStream_t st, bool* used) {
+    *used = false;
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("BMSP_HOST_GRAPH"); enabled = e ? atoi(e) : 1; }
+    if (!enabled) return BMSP_OK;
+    if (!(hp->gexec && hp->g_x == x_host && hp->g_y == y_host && hp->g_xdt == x_dtype)) {
+        const bool again = hp->seen_x == x_host && hp->seen_y == y_host && hp->seen_xdt == x_dtype;
+        hp->seen_x = x_host; hp->seen_y = y_host; hp->seen_xdt = x_dtype;
+        if (!again) return BMSP_OK;                        // first sight of these buffers: run eagerly
+        cudaPointerAttributes ax, ay;
+        if (cudaPointerGetAttributes(&ax, x_host) != cudaSuccess || cudaPointerGetAttributes(&ay, y_host) != cudaSuccess ||
+            ax.type != cudaMemoryTypeHost || ay.type != cudaMemoryTypeHost) { cudaGetLastError(); return BMSP_OK; }   // pageable: eager only
+        if (hp->gexec) { cudaGraphExecDestroy(hp->gexec); hp->gexec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        BMSP_CUDA(cudaStreamBeginCapture(hp->s_cap, cudaStreamCaptureModeThreadLocal));
+        const int rc = spmv_host_run<T>(A, hp, x_host, x_dtype, y_host, hp->s_cap);
+        const cudaError_t ce = cudaStreamEndCapture(hp->s_cap, &graph);
+        if (rc != BMSP_OK || ce != cudaSuccess || !graph) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); return BMSP_OK; }
+        const cudaError_t ie = cudaGraphInstantiate(&hp->gexec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { cudaGetLastError(); hp->gexec = nullptr; return BMSP_OK; }
+        hp->g_x = x_host; hp->g_y = y_host; hp->g_xdt = x_dtype;
+    }
+    BMSP_CUDA(cudaGraphLaunch(hp->gexec, st));
+    *used = true;
+    return BMSP_OK;
+}
+
 }  // namespace bmsp
 
 using namespace bmsp;
+
+extern "C" int bmsp_spmv_host(bmsp_matrix_t A, const void* x_host, int32_t x_dtype, float* y_host, void* stream) {
+    if (!A || !x_host || !y_host || (x_dtype != BMSP_F16 && x_dtype != BMSP_F32)) { set_error("bmsp_spmv_host: invalid argument"); return BMSP_ERR_INVALID; }
+    if (A->transposed) { set_error("bmsp_spmv_host: matrix is in transposed-operand form"); return BMSP_ERR_UNSUPPORTED; }
+    if (A->rows == 0) return BMSP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (A->spmv_path < 0) BMSP_TRY(plan_spmv(A, st));
+    HostPipe* hp = nullptr;
+    BMSP_TRY(host_pipe_get(A, st, &hp));
+    bool replayed = false;
+    if (A->dtype == BMSP_F16) BMSP_TRY(spmv_host_graph<__half>(A, hp, x_host, x_dtype, y_host, st, &replayed));
+    else BMSP_TRY(spmv_host_graph<float>(A, hp, x_host, x_dtype, y_host, st, &replayed));
+    if (replayed) return BMSP_OK;
+    return A->dtype == BMSP_F16 ? spmv_host_run<__half>(A, hp, x_host, x_dtype, y_host, st) : spmv_host_run<float>(A, hp, x_host, x_dtype, y_host, st);
+}
 
 extern "C" int bmsp_spmv(bmsp_matrix_t A, const void* x, int32_t x_dtype, float* y, void* stream) {
     if (!A || !x || !y || (x_dtype != BMSP_F16 && x_dtype != BMSP_F32)) { set_error("bmsp_spmv: invalid argument"); return BMSP_ERR_INVALID; }

@@ -28,6 +28,21 @@ def bmSparse_SpMV(A: bmSpMatrix, v: torch.Tensor, u: torch.Tensor | None = None,
     return u
 
 
+def bmSparse_SpMV_host(A: bmSpMatrix, v: torch.Tensor, u: torch.Tensor | None = None, stream=None):
+    """u = A v with v and u in HOST memory (pin them for full PCIe speed): what the reference's driver does by hand
+    around the operator (cudaMemcpy v, bmSparse_SpMV, cudaMemcpy u -- SPMV.cu:276-309), as one pipelined call.
+    u is complete after the stream (default: the current one) is synchronised."""
+    view = A._view()
+    if v.is_cuda or v.numel() != view.num_cols or not v.is_contiguous():
+        raise ValueError("v must be a contiguous host tensor with num_cols elements")
+    if u is None:
+        u = torch.empty(view.num_rows, dtype=torch.float32).pin_memory()
+    if u.is_cuda or u.dtype != torch.float32 or u.numel() != view.num_rows or not u.is_contiguous():
+        raise ValueError("u must be a contiguous host fp32 tensor with num_rows elements")
+    L.check(L.lib().bmsp_spmv_host(A._h, C.c_void_p(v.data_ptr()), _dt(v.dtype), C.c_void_p(u.data_ptr()), _stream_ptr(stream)))
+    return u
+
+
 def bmSparse_mult(A: bmSpMatrix, B: bmSpMatrix, C_out: bmSpMatrix | None = None, mode=0, VERBOSE: bool = False,
                   tc_version: int = 5, numeric_path: int = -1, brow_range=None, stream=None):
     """C = A * B with B in transposed-operand form (built with transpose=True, SPGEMM.cu:1262).

@@ -130,6 +130,13 @@ inline void bmSparse_SpMV_f32x(bmSpMatrix<ValueIn>& A, const float* v, float* u,
     bmsp::check(bmsp_spmv(A.handle(), v, BMSP_F32, u, stream));
 }
 
+/* The driver's copy-in / multiply / copy-out sequence (SPMV.cu:276-285, :299, :308-309) as one pipelined call: v and u are HOST
+ * pointers (pinned for full speed); u is complete once `stream` is synchronised. */
+template <class ValueIn>
+inline void bmSparse_SpMV_host(bmSpMatrix<ValueIn>& A, const float* v_host, float* u_host, void* stream = nullptr) {
+    bmsp::check(bmsp_spmv_host(A.handle(), v_host, BMSP_F32, u_host, stream));
+}
+
 /* bmSparse_mult<valueIn,valueOut>(A, B, C, mode, VERBOSE, tc_version), src/bmSparse_SPGEMM.cu:827-1223.  B must have been built
  * with transpose = true (SPGEMM.cu:1262).  mode / tc_version are accepted and ignored. */
 template <class valueIn, class valueOut>

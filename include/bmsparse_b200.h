@@ -137,6 +137,13 @@ int bmsp_compare(bmsp_matrix_t m, int64_t nnz, const int32_t* rows, const int32_
  * x: [num_cols] device, fp32 (x_dtype = BMSP_F32) or fp16; y: [num_rows] device fp32.
  * Asynchronous on `stream`; rows of empty block rows are written as 0. */
 int bmsp_spmv(bmsp_matrix_t A, const void* x, int32_t x_dtype, float* y, void* stream);
+/* y_host = A x_host with both vectors in HOST memory (pinned for full speed; pageable works but serialises).
+ * The reference's driver does this by hand around the operator: cudaMemcpy of v to the device, bmSparse_SpMV,
+ * cudaMemcpy of u back (SPMV.cu:276-285, :299, :308-309).  Here the three steps are one call and are pipelined:
+ * the block rows run in chunks, each chunk starts as soon as the x columns it touches have arrived and its y
+ * slice leaves while the next chunk runs (H2D and D2H share the full-duplex link).  Ordered after earlier work on
+ * `stream`; y_host is complete once `stream` is synchronised.  One call at a time per matrix. */
+int bmsp_spmv_host(bmsp_matrix_t A, const void* x_host, int32_t x_dtype, float* y_host, void* stream);
 /* Algorithmic bytes of one SpMV on the compact surface. */
 int bmsp_spmv_bytes(bmsp_matrix_t A, int32_t x_dtype, int64_t* bytes);
 

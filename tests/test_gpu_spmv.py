@@ -108,3 +108,44 @@ def test_full_size_poisson_properties(B):
     ref[1:, :] -= xg[:-1, :]; ref[:-1, :] -= xg[1:, :]; ref[:, 1:] -= xg[:, :-1]; ref[:, :-1] -= xg[:, 1:]
     assert (y1.double().view(m, m) - ref).abs().max().item() < 1e-5
     assert M.spmv_bytes() == 444452864
+
+
+def test_host_buffer_pipeline(B):
+    """bmsp_spmv_host (x and y in pinned host memory, chunked H2D / launch / D2H pipeline) == bmsp_spmv bit for bit,
+    on a banded matrix large enough to be chunked, a scattered one (first chunk needs all of x) and a path-1 matrix."""
+    G = B.generators
+    cases = [G.poisson5pt(640, 512), G.block_clustered(40000), G.uniform_random(300000, 8)]
+    rng = np.random.default_rng(9)
+    nr, nc = 400000, 400000           # scattered but dense-ish blocks: 8x8 blocks at random block positions
+    br = np.repeat(np.arange(nr // 8), 3); bc = rng.integers(0, nc // 8, br.size)
+    key = np.unique(br.astype(np.int64) * (nc // 8) + bc)
+    br, bc = key // (nc // 8), key % (nc // 8)
+    rows = (br[:, None, None] * 8 + np.arange(8)[None, :, None] + np.zeros((1, 1, 4), np.int64)).ravel()
+    cols = (bc[:, None, None] * 8 + np.zeros((1, 8, 1), np.int64) + np.array([0, 2, 5, 7])[None, None, :]).ravel()
+    o = np.lexsort((cols, rows)); rows, cols = rows[o], cols[o]
+    rp = np.zeros(nr + 1, np.int64); np.cumsum(np.bincount(rows, minlength=nr), out=rp[1:])
+    cases.append((nr, nc, rp.astype(np.int32), cols.astype(np.int32), rng.uniform(-1, 1, rows.size).astype(np.float16).astype(np.float32)))
+    for nr, nc, rp, ci, v in cases:
+        M = B.bmSpMatrix.from_csr(nr, nc, rp, ci, v)
+        for xdt in (torch.float32, torch.float16):
+            xh = torch.from_numpy(G.x_vector(nc)).to(xdt).pin_memory()
+            yh = torch.full((nr,), 7.0).pin_memory()
+            ref = B.bmSparse_SpMV(M, xh.cuda())
+            for it in range(4):       # 1st call eager, 2nd captures the pipeline as a CUDA graph, 3rd/4th replay it
+                yh.fill_(7.0)
+                B.bmSparse_SpMV_host(M, xh, yh)
+                torch.cuda.synchronize()
+                assert torch.equal(yh, ref.cpu()), (nr, xdt, it)
+            # other buffers after a capture: eager again, then re-captured
+            xh2 = (xh.float() * 0.5).to(xdt).pin_memory(); yh2 = torch.empty(nr).pin_memory()
+            ref2 = B.bmSparse_SpMV(M, xh2.cuda()).cpu()
+            for it in range(3):
+                B.bmSparse_SpMV_host(M, xh2, yh2)
+                torch.cuda.synchronize()
+                assert torch.equal(yh2, ref2), (nr, xdt, it)
+    # pageable host memory works too (slower)
+    nr, nc, rp, ci, v = cases[0]
+    M = B.bmSpMatrix.from_csr(nr, nc, rp, ci, v)
+    xh = torch.from_numpy(G.x_vector(nc)); yh = torch.empty(nr)
+    B.bmSparse_SpMV_host(M, xh, yh); torch.cuda.synchronize()
+    assert torch.equal(yh, B.bmSparse_SpMV(M, xh.cuda()).cpu())
