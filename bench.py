@@ -7,7 +7,8 @@ Headline (BASELINE.json configs[1]): bmSparse SpMV, fp16 values / fp32 x, y / fp
 2-D Poisson 4096x4096 grid (16.7M rows, 83.9M nnz) -- metric "SpMV HBM GB/s" = algorithmic bytes of the
 compact surface (nblk*12 + nbr*8 + nnz*2 + ncols*4 + nrows*4 = 444 452 864 B) / device time.
 A step = one SpMV.  N > 1 (torchrun, one rank per GPU): weak scaling, every rank owns one 4096x4096-grid
-slab of a 4096 x (4096 N) grid, x slices exchanged between neighbours over NCCL before every product.
+slab of a 4096 x (4096 N) grid; the SpMV kernel itself pushes its boundary rows of y into the neighbours' next x over
+NVLink peer memory (bmsp_spmv_halo; NCCL send/recv when peer mapping is unavailable or BMSP_BENCH_HALO=nccl).
 The same JSON line also carries the SpGEMM result (BASELINE configs[2], uniform-random 1M x 1M, 16 nnz/row,
 A*A, GFLOP/s including the symbolic phase) under "spgemm" -- measured on rank 0 at N = 1 only.
 
@@ -241,7 +242,8 @@ def main():
         vals = np.broadcast_to(np.array([-1, -1, 4, -1, -1], np.float32), (nr, 5))
         lrp = np.zeros(nr + 1, np.int64); np.cumsum(valid.sum(1), out=lrp[1:])
         bounds = np.arange(world + 1, dtype=np.int64) * nr
-        sharded = ShardedSpMV(bounds, (lrp.astype(np.int32), cols[valid], vals[valid].copy()), n_glob, device=dev)
+        sharded = ShardedSpMV(bounds, (lrp.astype(np.int32), cols[valid], vals[valid].copy()), n_glob, device=dev,
+                              halo=os.environ.get("BMSP_BENCH_HALO", "auto"))
         sharded.set_x(torch.from_numpy(x_host).to(dev))
         A = sharded.local
         conv_ms = None
@@ -277,7 +279,7 @@ def main():
     kern_ms = ms_step
     if world > 1:
         ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-        xb, yb = sharded.x[sharded.cur], sharded.own_slice(sharded.x[1 - sharded.cur])
+        xb, yb = sharded.x[sharded.cur], sharded.own_slice(sharded.x[(sharded.cur + 1) % len(sharded.x)])
         for _ in range(3):
             B.bmSparse_SpMV(A, xb, yb)
         ev0.record()
@@ -319,7 +321,9 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 values, f32 x/y/accumulate",
         "data": "synthetic",
         "config": {"workload": f"bmSparse SpMV, 2-D Poisson 5-point {GRID}x{GRID} grid per GPU ({nr} rows, {A.nnz} nnz, {A.block_num} 8x8 blocks)"
-                               + ("" if world == 1 else f"; global grid {GRID}x{GRID * world}, x halo exchange over NCCL each step ({sharded.halo_bytes} B in per rank)"),
+                               + ("" if world == 1 else f"; global grid {GRID}x{GRID * world}, x halo ({sharded.halo_bytes} B in per rank and step) "
+                                                             + ("pushed over NVLink peer memory by the SpMV kernel itself (bmsp_spmv_halo)" if sharded.p2p is not None
+                                                                else "exchanged with NCCL send/recv before each product")),
                    "algorithmic_bytes_per_step_per_gpu": nbytes,
                    "l2": "inputs larger than L2 (444 MB streamed per step vs 126 MB L2); no flush between steps",
                    "timing": "CUDA events on the launching stream around K steps, max over ranks"},
@@ -352,6 +356,8 @@ def main():
     if rank == 0:
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
+        sharded.check()
+        sharded.close()
         dist.destroy_process_group()
 
 

@@ -39,6 +39,15 @@ class SpgemmInfo(C.Structure):
                 ("c_nnz", C.c_int64), ("numeric_path", C.c_int32)]
 
 
+HALO_MAX = 8
+
+
+class HaloDesc(C.Structure):
+    _fields_ = [("n_push", C.c_int32), ("push_lo", C.c_int32 * HALO_MAX), ("push_hi", C.c_int32 * HALO_MAX),
+                ("push_dst", C.c_void_p * HALO_MAX), ("n_peer", C.c_int32), ("peer_flag", C.c_void_p * HALO_MAX),
+                ("my_flag", C.c_void_p * HALO_MAX), ("scratch", C.c_void_p), ("own_col_lo", C.c_int32), ("own_col_hi", C.c_int32)]
+
+
 class SpgemmOpts(C.Structure):
     _fields_ = [("mode", C.c_int32), ("tc_version", C.c_int32), ("verbose", C.c_int32), ("numeric_path", C.c_int32),
                 ("brow_begin", C.c_int32), ("brow_end", C.c_int32)]
@@ -48,7 +57,8 @@ class SpgemmOpts(C.Structure):
 SYMBOLS = ["bmsp_abi_version", "bmsp_last_error", "bmsp_device_info", "bmsp_create_from_csr", "bmsp_create_from_coo",
            "bmsp_create_from_mtx", "bmsp_create_from_arrays", "bmsp_destroy", "bmsp_get", "bmsp_download",
            "bmsp_to_coo", "bmsp_compare", "bmsp_spmv", "bmsp_spmv_host", "bmsp_spmv_bytes", "bmsp_spgemm", "bmsp_block_transpose",
-           "bmsp_partition_block_rows", "bmsp_slice_block_rows", "bmsp_debug_pair_bitmap"]
+           "bmsp_partition_block_rows", "bmsp_slice_block_rows", "bmsp_debug_pair_bitmap", "bmsp_spmv_halo", "bmsp_halo_push",
+           "bmsp_halo_status", "bmsp_peer_alloc", "bmsp_peer_open", "bmsp_peer_close", "bmsp_peer_free"]
 
 _lib = None
 

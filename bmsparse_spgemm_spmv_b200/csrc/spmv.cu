@@ -26,6 +26,9 @@
 #include <cstdlib>
 #include <algorithm>
 #include <vector>
+#include <cstring>
+#include <utility>
+#include <type_traits>
 
 namespace bmsp {
 
@@ -340,13 +343,112 @@ template <> __device__ __forceinline__ void sts_x<__half>(uint32_t a, __half v) 
 }
 template <typename X> struct alignas(4 * sizeof(X)) XQuad { X e[4]; };
 
+// ---- multi-GPU: halo exchange over peer memory (NVLink) fused into the product, SURVEY.md section 8e -------------
+// Every rank keeps x for its extended column range in three peer-mapped buffers (rotating) plus an inbox of epoch
+// flags, one slot per peer.  A product reads x[cur] (own slice + halo slices the peers pushed), writes y into the
+// own slice of x[nxt] and -- in the same kernel -- stores the rows a peer needs straight into that peer's x[nxt]
+// (P2P stores); the last pushing CTA then publishes `signal_epoch` in the peers' inboxes (st.release.sys after a
+// system fence).  Only tiles whose x lines leave the rank's own columns wait (spin on the inbox until every peer's
+// slot reached `wait_epoch`), and the tile order is rotated by half a grid so that these boundary tiles -- which
+// are also the ones that push -- run mid-kernel: the peers' rows of the previous product arrived long before, and
+// this product's rows are on their way long before the peers need them, so the exchange costs no time at all.
+// Peers signal each other in both directions even when one direction carries no data.  Write-after-read: the
+// buffer a peer overwrites during its product e was last read by my product e-2, which finished before my product
+// e-1 (whose epoch the peer waited for) started -- hence three buffers.
+constexpr int HALO_MAX = 8;
+struct HaloDev {
+    int32_t n_push, n_peer;
+    int32_t lo[HALO_MAX], hi[HALO_MAX];      // local row ranges [lo, hi) pushed to a peer (lo a multiple of 4)
+    float* dst[HALO_MAX];                    // peer address of row lo[i] (16-byte aligned)
+    uint32_t* peer_flag[HALO_MAX];           // my slot in each peer's inbox
+    const uint32_t* my_flag[HALO_MAX];       // the peers' slots in my inbox
+    uint32_t* scratch;                       // [0] pushing CTAs that finished, [1] error: a wait timed out
+    uint32_t wait_epoch, signal_epoch, n_sig;
+    int32_t solo_tile;                       // tile that signals when no tile pushes anything (-1: none)
+    int32_t own_c0, own_c1;                  // columns [own_c0, own_c1) of x_ext are this rank's own slice: tiles that stay inside never wait
+    int32_t rot;                             // tile order rotation: CTA b runs tile (b + rot) mod ntiles, so that the boundary tiles
+                                             // (which need the peers' rows and produce the rows the peers need) run mid-kernel
+};
+struct NoHalo {};
+
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// one thread per peer: spin until the peer's slot reached wait_epoch; gives up after 4 s (error flag, no hang)
+__device__ __forceinline__ void halo_wait(const HaloDev& h, int i) {
+    const uint32_t* f = h.my_flag[i];
+    if ((int32_t)(ld_relaxed_sys(f) - h.wait_epoch) < 0) {
+        const uint64_t t0 = globaltimer_ns();
+        while ((int32_t)(ld_relaxed_sys(f) - h.wait_epoch) < 0) {
+            if (*(volatile uint32_t*)(h.scratch + 1)) return;
+            if (globaltimer_ns() - t0 > 4000000000ull) { atomicExch(h.scratch + 1, 1u); return; }
+            __nanosleep(64);
+        }
+    }
+    fence_acq_rel_sys();        // the peer's rows were fenced before its flag: they are visible from here on
+}
+// one thread of every pushing CTA, after the CTA's remote stores were fenced (system scope) and barriered
+__device__ __forceinline__ void halo_signal(const HaloDev& h) {
+    const uint32_t old = atomicAdd(h.scratch, 1u);
+    if (old + 1u == h.n_sig) {
+        *(volatile uint32_t*)h.scratch = 0u;             // ready for the next launch
+        __threadfence_system();
+        for (int p = 0; p < h.n_peer; p++) st_release_sys(h.peer_flag[p], h.signal_epoch);
+    }
+}
+// rows [row, row + NR) of y (NR a multiple of 4 or the ragged tail) to every peer range that contains them
+template <int NR>
+__device__ __forceinline__ void halo_store(const HaloDev& h, int row, int rows, const float (&acc)[NR]) {
+    for (int i = 0; i < h.n_push; i++) {
+        const int lo = h.lo[i], hi = h.hi[i];
+        if (row >= hi || row + NR <= lo) continue;
+        float* d = h.dst[i] + (row - lo);
+        if (row >= lo && row + NR <= hi && row + NR <= rows) {
+#pragma unroll
+            for (int q = 0; q < NR; q += 4) *reinterpret_cast<float4*>(d + q) = make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NR; q++) if (row + q >= lo && row + q < hi && row + q < rows) d[q] = acc[q];
+        }
+    }
+}
+
+__global__ void halo_wait_kernel(const HaloDev h) {
+    if ((int)threadIdx.x < h.n_peer) halo_wait(h, threadIdx.x);
+}
+// stand-alone push (first exchange after set_x, and products that run the block-parallel kernel)
+__global__ void __launch_bounds__(256) halo_push_kernel(const float* __restrict__ y, const HaloDev h) {
+    for (int i = 0; i < h.n_push; i++) {
+        const int n = h.hi[i] - h.lo[i];
+        const float* src = y + h.lo[i];
+        float* d = h.dst[i];
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) d[k] = src[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) halo_signal(h);
+}
+
 // One CTA per tile of RTT block rows, TPR threads per block row (1: a thread owns all 8 matrix rows of its block
 // row; 2: one thread per 32-bit bitmap half).  Every thread reads the 32-byte tile descriptor; thread 0 arms the
 // mbarrier and issues the bulk copies (row pointers, bitmaps, x offsets, values) while all threads gather the
 // tile's distinct x lines (coalesced 16-byte loads, stored at a 33-element pitch); latency is hidden by the CTAs
 // resident per SM, each in a different phase.
-template <typename T, typename X, int RTT, int TPR, int MINB>
-__global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileArgs<T> a, const X* __restrict__ x, float* __restrict__ y) {
+// H = HaloDev: the multi-GPU variant (waits for the peers' halo slices before gathering x, pushes its boundary rows).
+template <typename T, typename X, int RTT, int TPR, int MINB, typename H = NoHalo>
+__global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileArgs<T> a, const X* __restrict__ x, float* __restrict__ y, const H hd) {
+    constexpr bool DIST = !std::is_same<H, NoHalo>::value;
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int VA = 16 / sizeof(T);   // values per 16 bytes
     constexpr int NT = RTT * TPR;
@@ -354,13 +456,15 @@ __global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileAr
     constexpr int GB = TPR == 1 ? 8 : 4; // gather steps in flight
     static_assert(NT >= 8 && NT % 8 == 0, "8 threads per x line");
     constexpr uint32_t SX = sizeof(X);
-    const int tid = threadIdx.x, t = blockIdx.x + a.tile0;
+    const int tid = threadIdx.x;
+    int t = blockIdx.x + a.tile0;
+    if constexpr (DIST) { t += hd.rot; if (t >= (int)gridDim.x) t -= (int)gridDim.x; }
     const uint32_t sbase = smem_u32(smem);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + a.so.bar);
 
     const int4* dp = reinterpret_cast<const int4*>(a.desc + t);
     const int4 d0 = __ldg(dp);
-    const int2 d1 = __ldg(reinterpret_cast<const int2*>(dp + 1));
+    const int4 d1 = __ldg(dp + 1);       // nl, flags, lmin, lmax
     const int p0 = d0.x, nb = d0.y, nv = d0.w, nl = d1.x;
     const uint32_t v0 = (uint32_t)d0.z, v0a = v0 & ~(uint32_t)(VA - 1);
     const bool staged = (d1.y & 1) && nb <= a.cap_blk && nv <= a.cap_val && nl <= a.cap_lines;
@@ -382,6 +486,14 @@ __global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileAr
         if (n8) bulk_g2s(smem, a.bmps + p0a, n8, bar);
         if (n2) bulk_g2s(smem + a.so.xo, a.xoff + p0x, n2, bar);
         if (nvb) bulk_g2s(smem + a.so.val, a.values + v0a, nvb, bar);
+    }
+    if constexpr (DIST) {
+        // Only a tile whose x lines leave this rank's own columns depends on the peers.  The matrix copies above are already
+        // in flight; x must not be touched before the halo is in.
+        if (nb > 0 && ((int64_t)d1.z * 32 < hd.own_c0 || ((int64_t)d1.w + 1) * 32 > hd.own_c1)) {
+            if (tid < hd.n_peer) halo_wait(hd, tid);
+            __syncthreads();
+        }
     }
     if (staged) {
         // x lines -> shared: 8 threads per line (4 elements each), GB steps of LPI lines in flight before the first store
@@ -421,35 +533,50 @@ __global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileAr
     const int lbr = tid / TPR, h = tid % TPR;
     constexpr int NR = 8 / TPR;      // matrix rows per thread
     const int row = (r0 + lbr) * 8 + h * NR;
-    if (lbr >= nrow || row >= a.rows) return;
+    const bool active = lbr < nrow && row < a.rows;
+    if (!DIST && !active) return;
     float acc[NR];
 #pragma unroll
     for (int q = 0; q < NR; q++) acc[q] = 0.f;
-    const uint2 rp = lds_v2(sbase + a.so.row + 8u * lbr);          // (first block, first value) of this block row
-    const uint32_t pe = lds_u32(sbase + a.so.row + 8u * lbr + 8u);
-    const uint32_t pb = rp.x, kv = rp.y;
-    if (staged) {
-        const uint32_t rel = pb - (uint32_t)p0;
-        const uint32_t a_bm = sbase + ((uint32_t)(p0 & 1) + rel) * 8u, a_xo = sbase + a.so.xo + ((uint32_t)(p0 & 7) + rel) * 2u;
-        const uint32_t a_v = sbase + a.so.val + (kv - v0a) * (uint32_t)sizeof(T), xs31 = sbase + a.so.xs + 31u * SX;
-        if constexpr (TPR == 2) tile_half_row<T, X>(a_bm, a_xo, a_v, (int)(pe - pb), h, xs31, acc);
-        else tile_block_row<T, X>(a_bm, a_xo, a_v, (int)(pe - pb), xs31, acc);
-    } else if constexpr (TPR == 2) {
-        half_block_row<T, X>(a.bmps, a.bcol, a.values, (int)pb, (int)pe, kv, h, x, acc);
-    } else {
-        float lo4[4] = {0.f, 0.f, 0.f, 0.f}, hi4[4] = {0.f, 0.f, 0.f, 0.f};
-        half_block_row<T, X>(a.bmps, a.bcol, a.values, (int)pb, (int)pe, kv, 0, x, lo4);
-        half_block_row<T, X>(a.bmps, a.bcol, a.values, (int)pb, (int)pe, kv, 1, x, hi4);
+    if (active) {
+        const uint2 rp = lds_v2(sbase + a.so.row + 8u * lbr);          // (first block, first value) of this block row
+        const uint32_t pe = lds_u32(sbase + a.so.row + 8u * lbr + 8u);
+        const uint32_t pb = rp.x, kv = rp.y;
+        if (staged) {
+            const uint32_t rel = pb - (uint32_t)p0;
+            const uint32_t a_bm = sbase + ((uint32_t)(p0 & 1) + rel) * 8u, a_xo = sbase + a.so.xo + ((uint32_t)(p0 & 7) + rel) * 2u;
+            const uint32_t a_v = sbase + a.so.val + (kv - v0a) * (uint32_t)sizeof(T), xs31 = sbase + a.so.xs + 31u * SX;
+            if constexpr (TPR == 2) tile_half_row<T, X>(a_bm, a_xo, a_v, (int)(pe - pb), h, xs31, acc);
+            else tile_block_row<T, X>(a_bm, a_xo, a_v, (int)(pe - pb), xs31, acc);
+        } else if constexpr (TPR == 2) {
+            half_block_row<T, X>(a.bmps, a.bcol, a.values, (int)pb, (int)pe, kv, h, x, acc);
+        } else {
+            float lo4[4] = {0.f, 0.f, 0.f, 0.f}, hi4[4] = {0.f, 0.f, 0.f, 0.f};
+            half_block_row<T, X>(a.bmps, a.bcol, a.values, (int)pb, (int)pe, kv, 0, x, lo4);
+            half_block_row<T, X>(a.bmps, a.bcol, a.values, (int)pb, (int)pe, kv, 1, x, hi4);
 #pragma unroll
-        for (int q = 0; q < 4; q++) { acc[q] = lo4[q]; acc[4 + q] = hi4[q]; }
+            for (int q = 0; q < 4; q++) { acc[q] = lo4[q]; acc[4 + q] = hi4[q]; }
+        }
+        float* yr = y + row;
+        if (row + NR <= a.rows) {
+#pragma unroll
+            for (int q = 0; q < NR; q += 4) *reinterpret_cast<float4*>(yr + q) = make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NR; q++) if (row + q < a.rows) yr[q] = acc[q];
+        }
     }
-    float* yr = y + row;
-    if (row + NR <= a.rows) {
-#pragma unroll
-        for (int q = 0; q < NR; q += 4) *reinterpret_cast<float4*>(yr + q) = make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
-    } else {
-#pragma unroll
-        for (int q = 0; q < NR; q++) if (row + q < a.rows) yr[q] = acc[q];
+    if constexpr (DIST) {
+        // does this tile own rows a peer needs?  (CTA-uniform)
+        const int trow0 = r0 * 8, trow1 = min(a.rows, (r0 + nrow) * 8);
+        bool part = t == hd.solo_tile;
+        for (int i = 0; i < hd.n_push; i++) part |= hd.lo[i] < trow1 && hd.hi[i] > trow0;
+        if (part) {
+            if (active) halo_store<NR>(hd, row, a.rows, acc);
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) halo_signal(hd);
+        }
     }
 }
 
@@ -609,9 +736,24 @@ int plan_spmv(bmsp_matrix_s* m, cudaStream_t st) {
     return BMSP_OK;
 }
 
-// tile0 / ntiles: path 0 only -- launch the tiles [tile0, tile0 + ntiles) (ntiles < 0: all of them)
-template <typename T, typename X>
-static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, int tile0 = 0, int ntiles = -1) {
+template <typename T, typename X, int RTT, int TPR, int MINB, typename H>
+static int launch_tile_kernel(const TileArgs<T>& a, const X* x, float* y, const H& hd, int grid, size_t smem, cudaStream_t st) {
+    auto kern = spmv_tile_kernel<T, X, RTT, TPR, MINB, H>;
+    static size_t configured = 0;            // per instantiation
+    if (configured < smem || configured == 0) {
+        BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured = std::max<size_t>(smem, 1);
+    }
+    kern<<<(unsigned)grid, RTT * TPR, smem, st>>>(a, x, y, hd);
+    BMSP_KERNEL_CHECK();
+    return BMSP_OK;
+}
+
+// tile0 / ntiles: path 0 only -- launch the tiles [tile0, tile0 + ntiles) (ntiles < 0: all of them).
+// hd: NoHalo, or HaloDev for the fused multi-GPU product (path 0, fp32 x, all tiles).
+template <typename T, typename X, typename H = NoHalo>
+static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, int tile0 = 0, int ntiles = -1, const H& hd = H()) {
     if (A->spmv_path == 0) {
         TileArgs<T> a;
         a.tile0 = tile0;
@@ -621,26 +763,17 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, 
         const int rt = A->tile_rows;
         a.so = tile_smem(rt, a.cap_blk, a.cap_val, a.cap_lines, sizeof(T), sizeof(X));
         const size_t smem = a.so.total;
-        // default: one thread per bitmap half; BMSP_SPMV_VARIANT=1: one thread per block row (64-row tiles only).
-        // Measured on P4096: 92.7 us vs 103.5 us (fewer instructions, but too few warps to hide the staging latency).
-        void (*kern)(TileArgs<T>, const X*, float*) = spmv_tile_kernel<T, X, 64, 2, 12>;
-        int nthreads = 2 * rt;
-        if (rt == 32) kern = spmv_tile_kernel<T, X, 32, 2, 24>;
-        else if (rt == 16) kern = spmv_tile_kernel<T, X, 16, 2, 32>;
-        else if (spmv_variant() == 1) { kern = spmv_tile_kernel<T, X, 64, 1, 14>; nthreads = rt; }
-        else if (spmv_variant() == 3) kern = spmv_tile_kernel<T, X, 64, 2, 14>;
-        static size_t configured = 0;
-        static void* configured_for = nullptr;
-        if (configured < smem || configured_for != (void*)kern) {
-            BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-            BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            configured = smem; configured_for = (void*)kern;
-        }
         const int grid = ntiles < 0 ? (int)ceil_div(A->nbr, rt) : ntiles;
         if (grid <= 0) return BMSP_OK;
-        kern<<<(unsigned)grid, nthreads, smem, st>>>(a, x, y);
-        BMSP_KERNEL_CHECK();
-        return BMSP_OK;
+        // default: one thread per bitmap half; BMSP_SPMV_VARIANT=1: one thread per block row (64-row tiles only).
+        // Measured on P4096: 92.7 us vs 103.5 us (fewer instructions, but too few warps to hide the staging latency).
+        if (rt == 32) return launch_tile_kernel<T, X, 32, 2, 24, H>(a, x, y, hd, grid, smem, st);
+        if (rt == 16) return launch_tile_kernel<T, X, 16, 2, 32, H>(a, x, y, hd, grid, smem, st);
+        if constexpr (std::is_same<H, NoHalo>::value) {
+            if (spmv_variant() == 1) return launch_tile_kernel<T, X, 64, 1, 14, H>(a, x, y, hd, grid, smem, st);
+            if (spmv_variant() == 3) return launch_tile_kernel<T, X, 64, 2, 14, H>(a, x, y, hd, grid, smem, st);
+        }
+        return launch_tile_kernel<T, X, 64, 2, 12, H>(a, x, y, hd, grid, smem, st);
     }
     spmv_blockpar_kernel<T, X><<<(unsigned)ceil_div(A->n_work, 8), 256, 0, st>>>(A->bmps, A->bcol, A->offsets, (const T*)A->values,
                                                                                (const int4*)A->work, A->n_work, A->rows, x, y,
@@ -731,9 +864,24 @@ void spmv_host_release(bmsp_matrix_s* m) {
     m->host_pipe = nullptr;
 }
 
+// y can leave without a copy engine: when y_host is pinned (and therefore mapped into the device's address space) the
+// row-range launches store their float4 results straight into it over PCIe (posted writes), so the pipeline is
+// H2D slices of x on s_in against kernels that write host memory -- no D2H copies, no events per chunk on the way out.
+static float* mapped_host_ptr(float* y_host) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("BMSP_HOST_ZEROCOPY"); enabled = e ? atoi(e) : 1; }
+    if (!enabled) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, y_host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer || ((uintptr_t)at.devicePointer & 15)) return nullptr;
+    return (float*)at.devicePointer;
+}
+
 template <typename T>
 static int spmv_host_run(bmsp_matrix_s* A, HostPipe* hp, const void* x_host, int32_t x_dtype, float* y_host, cudaStream_t st) {
     const size_t xs = x_dtype == BMSP_F16 ? 2 : 4;
+    float* y_map = A->spmv_path == 0 ? mapped_host_ptr(y_host) : nullptr;     // row-tiled kernel only: it stores 512 contiguous bytes per warp
+    float* y_out = y_map ? y_map : hp->y_dev;
     BMSP_CUDA(cudaEventRecord(hp->ev_start, st));         // earlier work on st (and the previous call) is done with x_dev / y_dev
     BMSP_CUDA(cudaStreamWaitEvent(hp->s_in, hp->ev_start, 0));
     BMSP_CUDA(cudaStreamWaitEvent(hp->s_out, hp->ev_start, 0));
@@ -753,13 +901,13 @@ static int spmv_host_run(bmsp_matrix_s* A, HostPipe* hp, const void* x_host, int
         if (A->spmv_path == 0) {
             const int t0 = hp->tile_lo[c], t1 = hp->tile_lo[c + 1];
             row0 = std::min<int64_t>(A->rows, t0 * rows_per_tile); row1 = std::min<int64_t>(A->rows, t1 * rows_per_tile);
-            if (x_dtype == BMSP_F32) BMSP_TRY((launch_spmv<T, float>(A, (const float*)hp->x_dev, hp->y_dev, st, t0, t1 - t0)));
-            else BMSP_TRY((launch_spmv<T, __half>(A, (const __half*)hp->x_dev, hp->y_dev, st, t0, t1 - t0)));
+            if (x_dtype == BMSP_F32) BMSP_TRY((launch_spmv<T, float>(A, (const float*)hp->x_dev, y_out, st, t0, t1 - t0)));
+            else BMSP_TRY((launch_spmv<T, __half>(A, (const __half*)hp->x_dev, y_out, st, t0, t1 - t0)));
         } else {
-            if (x_dtype == BMSP_F32) BMSP_TRY((launch_spmv<T, float>(A, (const float*)hp->x_dev, hp->y_dev, st)));
-            else BMSP_TRY((launch_spmv<T, __half>(A, (const __half*)hp->x_dev, hp->y_dev, st)));
+            if (x_dtype == BMSP_F32) BMSP_TRY((launch_spmv<T, float>(A, (const float*)hp->x_dev, y_out, st)));
+            else BMSP_TRY((launch_spmv<T, __half>(A, (const __half*)hp->x_dev, y_out, st)));
         }
-        if (row1 > row0) {
+        if (row1 > row0 && !y_map) {
             BMSP_CUDA(cudaEventRecord(hp->ev_k[c], st));
             BMSP_CUDA(cudaStreamWaitEvent(hp->s_out, hp->ev_k[c], 0));
             BMSP_CUDA(cudaMemcpyAsync(y_host + row0, hp->y_dev + row0, (size_t)(row1 - row0) * 4, cudaMemcpyDeviceToHost, hp->s_out));
@@ -820,6 +968,113 @@ extern "C" int bmsp_spmv_host(bmsp_matrix_t A, const void* x_host, int32_t x_dty
     if (replayed) return BMSP_OK;
     return A->dtype == BMSP_F16 ? spmv_host_run<__half>(A, hp, x_host, x_dtype, y_host, st) : spmv_host_run<float>(A, hp, x_host, x_dtype, y_host, st);
 }
+
+namespace bmsp {
+
+// ---- multi-GPU product with the halo exchange over peer memory ---------------------------------------------------
+static int halo_to_dev(const bmsp_halo_desc* d, int rows, HaloDev* h) {
+    if (!d || d->n_push < 0 || d->n_push > HALO_MAX || d->n_peer < 0 || d->n_peer > HALO_MAX || (d->n_peer > 0 && !d->scratch)) {
+        set_error("halo descriptor: bad counts or missing scratch"); return BMSP_ERR_INVALID;
+    }
+    memset(h, 0, sizeof(*h));
+    h->n_push = d->n_push; h->n_peer = d->n_peer; h->scratch = (uint32_t*)d->scratch; h->solo_tile = -1;
+    h->own_c0 = d->own_col_lo; h->own_c1 = d->own_col_hi;
+    for (int i = 0; i < d->n_push; i++) {
+        if (d->push_lo[i] < 0 || d->push_hi[i] > rows || d->push_lo[i] > d->push_hi[i] || (d->push_lo[i] & 3) || ((uintptr_t)d->push_dst[i] & 15)) {
+            set_error("halo descriptor: push range %d [%d,%d) invalid or misaligned", i, d->push_lo[i], d->push_hi[i]); return BMSP_ERR_INVALID;
+        }
+        h->lo[i] = d->push_lo[i]; h->hi[i] = d->push_hi[i]; h->dst[i] = (float*)d->push_dst[i];
+    }
+    for (int i = 0; i < d->n_peer; i++) { h->peer_flag[i] = (uint32_t*)d->peer_flag[i]; h->my_flag[i] = (const uint32_t*)d->my_flag[i]; }
+    return BMSP_OK;
+}
+
+}  // namespace bmsp
+using namespace bmsp;
+
+extern "C" int bmsp_halo_push(const float* y_own, int32_t rows, const bmsp_halo_desc* halo, uint32_t signal_epoch, void* stream) {
+    if (!y_own) { set_error("bmsp_halo_push: null vector"); return BMSP_ERR_INVALID; }
+    HaloDev h;
+    BMSP_TRY(halo_to_dev(halo, rows, &h));
+    if (h.n_peer == 0) return BMSP_OK;
+    int64_t total = 0;
+    for (int i = 0; i < h.n_push; i++) total += h.hi[i] - h.lo[i];
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 1024), 592));
+    h.signal_epoch = signal_epoch; h.n_sig = (uint32_t)grid;
+    halo_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y_own, h);
+    BMSP_KERNEL_CHECK();
+    return BMSP_OK;
+}
+
+extern "C" int bmsp_halo_status(const bmsp_halo_desc* halo, void* stream, int32_t* timed_out) {
+    if (!halo || !timed_out) { set_error("bmsp_halo_status: null argument"); return BMSP_ERR_INVALID; }
+    uint32_t v[2] = {0, 0};
+    if (halo->scratch) {
+        BMSP_CUDA(cudaMemcpyAsync(v, halo->scratch, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        BMSP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    }
+    *timed_out = (int32_t)v[1];
+    return BMSP_OK;
+}
+
+extern "C" int bmsp_spmv_halo(bmsp_matrix_t A, const float* x_ext, float* y_own, const bmsp_halo_desc* halo, uint32_t wait_epoch,
+                              uint32_t signal_epoch, void* stream) {
+    if (!A || !x_ext || !y_own) { set_error("bmsp_spmv_halo: null argument"); return BMSP_ERR_INVALID; }
+    if (A->transposed) { set_error("bmsp_spmv_halo: matrix is in transposed-operand form"); return BMSP_ERR_UNSUPPORTED; }
+    if (((uintptr_t)x_ext & 15) || ((uintptr_t)y_own & 15)) { set_error("bmsp_spmv_halo: x and y must be 16-byte aligned"); return BMSP_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    HaloDev h;
+    BMSP_TRY(halo_to_dev(halo, A->rows, &h));
+    h.wait_epoch = wait_epoch; h.signal_epoch = signal_epoch;
+    if (A->rows == 0 || h.n_peer == 0) return A->rows == 0 ? BMSP_OK : bmsp_spmv(A, x_ext, BMSP_F32, y_own, stream);
+    if (A->spmv_path < 0) BMSP_TRY(plan_spmv(A, st));
+    static int fused = -1;
+    if (fused < 0) { const char* e = getenv("BMSP_HALO_FUSED"); fused = e ? atoi(e) : 1; }
+    if (A->spmv_path == 0 && fused) {
+        // tiles that own pushed rows (union of the ranges' tile intervals); they count down to the signal
+        const int64_t rpt = (int64_t)A->tile_rows * 8;
+        std::vector<std::pair<int64_t, int64_t>> iv;
+        for (int i = 0; i < h.n_push; i++) if (h.hi[i] > h.lo[i]) iv.push_back({h.lo[i] / rpt, (h.hi[i] - 1) / rpt});
+        std::sort(iv.begin(), iv.end());
+        int64_t n = 0, reach = -1;
+        for (auto& p : iv) { const int64_t a0 = std::max(p.first, reach + 1); if (p.second >= a0) { n += p.second - a0 + 1; reach = p.second; } }
+        if (n == 0) { h.solo_tile = 0; n = 1; }
+        h.n_sig = (uint32_t)n;
+        static int rotate = -1;
+        if (rotate < 0) { const char* e = getenv("BMSP_HALO_ROTATE"); rotate = e ? atoi(e) : 1; }
+        h.rot = rotate ? (int)(ceil_div(A->nbr, A->tile_rows) / 2) : 0;
+        return A->dtype == BMSP_F16 ? launch_spmv<__half, float, HaloDev>(A, x_ext, y_own, st, 0, -1, h)
+                                    : launch_spmv<float, float, HaloDev>(A, x_ext, y_own, st, 0, -1, h);
+    }
+    // block-parallel path (or BMSP_HALO_FUSED=0): wait kernel, product, push kernel
+    halo_wait_kernel<<<1, 32, 0, st>>>(h);
+    BMSP_KERNEL_CHECK();
+    BMSP_TRY(bmsp_spmv(A, x_ext, BMSP_F32, y_own, stream));
+    return bmsp_halo_push(y_own, A->rows, halo, signal_epoch, stream);
+}
+
+// ---- peer-mapped device memory for the halo buffers (one process per GPU: CUDA IPC handles travel through the caller) ----
+extern "C" int bmsp_peer_alloc(int64_t bytes, void** ptr, void* handle64) {
+    if (!ptr || !handle64 || bytes <= 0) { set_error("bmsp_peer_alloc: invalid argument"); return BMSP_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    *ptr = nullptr;
+    BMSP_CUDA(cudaMalloc(ptr, (size_t)bytes));          // IPC needs a plain allocation, not the stream-ordered pool
+    BMSP_CUDA(cudaMemset(*ptr, 0, (size_t)bytes));
+    cudaIpcMemHandle_t hd;
+    BMSP_CUDA(cudaIpcGetMemHandle(&hd, *ptr));
+    memcpy(handle64, &hd, 64);
+    return BMSP_OK;
+}
+extern "C" int bmsp_peer_open(const void* handle64, void** ptr) {
+    if (!ptr || !handle64) { set_error("bmsp_peer_open: invalid argument"); return BMSP_ERR_INVALID; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    *ptr = nullptr;
+    BMSP_CUDA(cudaIpcOpenMemHandle(ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return BMSP_OK;
+}
+extern "C" int bmsp_peer_close(void* ptr) { if (ptr) BMSP_CUDA(cudaIpcCloseMemHandle(ptr)); return BMSP_OK; }
+extern "C" int bmsp_peer_free(void* ptr) { if (ptr) BMSP_CUDA(cudaFree(ptr)); return BMSP_OK; }
 
 extern "C" int bmsp_spmv(bmsp_matrix_t A, const void* x, int32_t x_dtype, float* y, void* stream) {
     if (!A || !x || !y || (x_dtype != BMSP_F16 && x_dtype != BMSP_F32)) { set_error("bmsp_spmv: invalid argument"); return BMSP_ERR_INVALID; }

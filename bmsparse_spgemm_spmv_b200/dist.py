@@ -6,8 +6,8 @@ north star adds.  Both operators shard by block rows and need no reduction:
   SpMV    rank r owns a contiguous range of block rows and the matching slice of x / y.  Before each
           product it fetches only the slices of x its block columns touch ("range halo": for a banded
           matrix two neighbours, for a scattered one everybody -- then it degenerates to an all-gather).
-          y is written straight into the owner's slice of the next x, so repeated products ping-pong
-          between two buffers with no copy.
+          y is written straight into the owner's slice of the next x, so repeated products rotate
+          through two (NCCL) or three (peer memory) buffers with no copy.
   SpGEMM  rank r multiplies its block rows of A by a replicated B^t (bmSparse_mult(..., brow_range)); the
           concatenation of the per-rank C arrays is bit-identical to the single-GPU product.
 """
@@ -49,8 +49,9 @@ class ShardedSpMV:
                  current CUDA device and calls bmSparse_SpMV (the CPU tests inject the oracle here)
     """
 
-    def __init__(self, row_bounds, local_csr, n_cols, group=None, device=None, spmv_fn=None, build_fn=None):
+    def __init__(self, row_bounds, local_csr, n_cols, group=None, device=None, spmv_fn=None, build_fn=None, halo="auto"):
         self.group = group
+        self.p2p = None                      # PeerHalo when the exchange runs over peer memory inside the SpMV kernel
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.bounds = np.asarray(row_bounds, np.int64)
@@ -78,8 +79,16 @@ class ShardedSpMV:
             if a < b:
                 self.send.append((p, a, b))
         n_ext = self.ext_hi - self.ext_lo
-        self.x = [torch.zeros(n_ext, dtype=torch.float32, device=self.device) for _ in range(2)]
         self.cur = 0
+        self.x = None
+        if halo != "nccl" and spmv_fn is None and self.device.type == "cuda" and self.world > 1:
+            self.p2p = PeerHalo.create(self, ranges, n_ext)          # collective; None when any rank cannot map its peers
+            if self.p2p is None and halo == "p2p":
+                raise RuntimeError("peer-memory halo exchange requested but not available")
+        if self.p2p is not None:
+            self.x = self.p2p.x
+        else:
+            self.x = [torch.zeros(n_ext, dtype=torch.float32, device=self.device) for _ in range(2)]
         self.halo_bytes = sum(b - a for _, a, b in self.recv) * 4
         local_ci = (np.asarray(ci, np.int64) - self.ext_lo).astype(np.int32)
         n_rows = self.own_hi - self.own_lo
@@ -96,7 +105,10 @@ class ShardedSpMV:
         return buf[self.own_lo - self.ext_lo: self.own_hi - self.ext_lo]
 
     def set_x(self, x_own: torch.Tensor):
+        """collective: every rank sets its slice of x (then, in peer-memory mode, pushes it to the peers that need it)"""
         self.own_slice(self.x[self.cur]).copy_(x_own)
+        if self.p2p is not None:
+            self.p2p.first_push(self)
 
     def exchange(self):
         """fetch the halo slices of the current x from their owners (NCCL send/recv over NVLink)."""
@@ -111,14 +123,141 @@ class ShardedSpMV:
                 w.wait()
 
     def step(self):
-        """one product: halo exchange of x, then y = A_local x_ext written into the next x's own slice."""
-        self.exchange()
-        nxt = 1 - self.cur
-        self._spmv(self.x[self.cur], self.own_slice(self.x[nxt]))
+        """one product: halo exchange of x, then y = A_local x_ext written into the next x's own slice.
+        Peer-memory mode: one kernel does all of it (wait for the peers' epoch, product, P2P stores of the boundary rows
+        into the peers' next x, publish the next epoch)."""
+        nxt = (self.cur + 1) % len(self.x)
+        if self.p2p is not None:
+            self.p2p.step(self, nxt)
+        else:
+            self.exchange()
+            self._spmv(self.x[self.cur], self.own_slice(self.x[nxt]))
         self.cur = nxt
+
+    def check(self):
+        """raises if a peer-memory wait timed out (a peer died); no-op in NCCL mode"""
+        if self.p2p is not None:
+            self.p2p.check()
+
+    def close(self):
+        if self.p2p is not None:
+            self.p2p.close(self)
+            self.p2p = None
 
     def y_own(self):
         return self.own_slice(self.x[self.cur])
+
+
+class PeerHalo:
+    """Peer-mapped ping-pong x buffers + epoch inbox of one rank, and the bmsp_halo_desc of each buffer.
+
+    Region layout (one cudaMalloc per rank, exported as a CUDA IPC handle and opened by the ranks that talk to it):
+        [0, 1024)            inbox: uint32 epoch slot per source rank
+        [1024, 1024+S)       x buffer 0 (n_ext fp32, S = n_ext*4 rounded up to 256)
+        [1024+S, 1024+2S)    x buffer 1
+        [1024+2S, 1024+3S)   x buffer 2
+    Three buffers, not two: the kernel publishes its epoch as soon as its boundary tiles are done (mid-kernel, see the tile
+    rotation in spmv.cu), so a peer may start writing the next-but-one x while this rank's kernel still reads the current
+    one; with three buffers the buffer being overwritten is always one whose last reader finished a whole launch earlier.
+    """
+    INBOX = 1024
+    NBUF = 3
+
+    @classmethod
+    def create(cls, sh, ranges, n_ext):
+        import ctypes as C
+        from . import _lib as L
+        from .matrix import _alias
+        self = cls()
+        self.epoch = 0
+        self.opened = {}
+        self.base = None
+        ok = True
+        try:
+            peers = sorted({p for p, _, _ in sh.send} | {p for p, _, _ in sh.recv})
+            if len(peers) > L.HALO_MAX or len(sh.send) > L.HALO_MAX or sh.world > cls.INBOX // 4:
+                raise RuntimeError("too many peers for one halo descriptor")
+            stride = (n_ext * 4 + 255) // 256 * 256
+            base = C.c_void_p(); handle = (C.c_ubyte * 64)()
+            L.check(L.lib().bmsp_peer_alloc(C.c_int64(cls.INBOX + cls.NBUF * stride), C.byref(base), handle))
+            self.base, self.stride = base.value, stride
+        except Exception as e:  # noqa: BLE001 -- every rank must reach the all_gather below
+            ok, handle, stride, peers = False, None, 0, []
+            self.err = e
+        info = [None] * sh.world
+        dist.all_gather_object(info, {"ok": ok, "handle": bytes(handle) if ok else b"", "stride": stride, "ext_lo": sh.ext_lo}, group=sh.group)
+        if ok and all(i["ok"] for i in info):
+            try:
+                for p in peers:
+                    ptr = C.c_void_p()
+                    L.check(L.lib().bmsp_peer_open((C.c_ubyte * 64).from_buffer_copy(info[p]["handle"]), C.byref(ptr)))
+                    self.opened[p] = ptr.value
+            except Exception as e:  # noqa: BLE001
+                ok = False
+                self.err = e
+        flag = torch.tensor([1 if ok and all(i["ok"] for i in info) else 0], device=sh.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=sh.group)
+        if int(flag.item()) == 0:
+            self._release()
+            return None
+        self.x = [_alias(self.base + cls.INBOX + b * stride, n_ext, "<f4", torch.float32, self) for b in range(cls.NBUF)]
+        self.scratch = torch.zeros(4, dtype=torch.int32, device=sh.device)
+        self.desc = []
+        for b in range(cls.NBUF):
+            d = L.HaloDesc()
+            d.n_push = len(sh.send)
+            for i, (p, a, e) in enumerate(sh.send):
+                d.push_lo[i] = a - sh.own_lo; d.push_hi[i] = e - sh.own_lo
+                d.push_dst[i] = self.opened[p] + cls.INBOX + b * info[p]["stride"] + (a - info[p]["ext_lo"]) * 4
+            d.n_peer = len(peers)
+            for i, p in enumerate(peers):
+                d.peer_flag[i] = self.opened[p] + 4 * sh.rank
+                d.my_flag[i] = self.base + 4 * p
+            d.scratch = self.scratch.data_ptr()
+            d.own_col_lo = sh.own_lo - sh.ext_lo; d.own_col_hi = sh.own_hi - sh.ext_lo
+            self.desc.append(d)
+        return self
+
+    def first_push(self, sh):
+        import ctypes as C
+        from . import _lib as L
+        from .matrix import _stream_ptr
+        torch.cuda.synchronize(); dist.barrier(group=sh.group)        # nobody still reads the buffer we are about to fill
+        self.epoch += 1
+        own = sh.own_slice(self.x[sh.cur])
+        L.check(L.lib().bmsp_halo_push(C.c_void_p(own.data_ptr()), own.numel(), C.byref(self.desc[sh.cur]), C.c_uint32(self.epoch), _stream_ptr()))
+
+    def step(self, sh, nxt):
+        import ctypes as C
+        from . import _lib as L
+        from .matrix import _stream_ptr
+        L.check(L.lib().bmsp_spmv_halo(sh.local._h, C.c_void_p(self.x[sh.cur].data_ptr()), C.c_void_p(sh.own_slice(self.x[nxt]).data_ptr()),
+                                       C.byref(self.desc[nxt]), C.c_uint32(self.epoch), C.c_uint32(self.epoch + 1), _stream_ptr()))
+        self.epoch += 1
+
+    def check(self):
+        import ctypes as C
+        from . import _lib as L
+        from .matrix import _stream_ptr
+        t = C.c_int32()
+        L.check(L.lib().bmsp_halo_status(C.byref(self.desc[0]), _stream_ptr(), C.byref(t)))
+        if t.value:
+            raise RuntimeError("peer-memory halo exchange: a wait timed out (peer lost)")
+
+    def _release(self):
+        from . import _lib as L
+        import ctypes as C
+        for ptr in self.opened.values():
+            L.lib().bmsp_peer_close(C.c_void_p(ptr))
+        self.opened = {}
+        if self.base:
+            L.lib().bmsp_peer_free(C.c_void_p(self.base))
+            self.base = None
+
+    def close(self, sh):
+        torch.cuda.synchronize(); dist.barrier(group=sh.group)        # no peer still writes into my region
+        self.x = None
+        self._release()
 
 
 def broadcast_matrix(M, src: int = 0, group=None):

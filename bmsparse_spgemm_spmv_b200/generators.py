@@ -117,5 +117,65 @@ def rmat(scale: int, edge_factor: int = 16, a=0.57, b=0.19, c=0.19, seed: int = 
     return n, n, rp.astype(np.int32), col.astype(np.int32), values_fp16(seed, key.size)
 
 
+# ---- the same counter-based generators evaluated with torch (on the GPU for the big configs: rmat(22) takes minutes in numpy) ----
+def _t_lsr(z, k):
+    """logical shift right of int64 bit patterns"""
+    return (z >> k) & ((1 << (64 - k)) - 1)
+
+
+def _t_i64(c: int) -> int:
+    """uint64 constant as the int64 with the same bits"""
+    return c - (1 << 64) if c >= (1 << 63) else c
+
+
+def splitmix64_torch(seed: int, idx):
+    """splitmix64() above on torch int64 tensors (two's-complement wrap-around == uint64 arithmetic); returns int64 bit patterns."""
+    z = (idx + 1) * _t_i64(0x9E3779B97F4A7C15) + _t_i64(seed & 0xFFFFFFFFFFFFFFFF)
+    z = (z ^ _t_lsr(z, 30)) * _t_i64(0xBF58476D1CE4E5B9)
+    z = (z ^ _t_lsr(z, 27)) * _t_i64(0x94D049BB133111EB)
+    return z ^ _t_lsr(z, 31)
+
+
+def _unit_torch(seed: int, idx):
+    import torch
+    return _t_lsr(splitmix64_torch(seed, idx), 11).to(torch.float64) * (1.0 / (1 << 53))
+
+
+def values_fp16_torch(seed: int, n: int, device):
+    import torch
+    v = _unit_torch(seed ^ 0x5EED, torch.arange(n, dtype=torch.int64, device=device)) * 2.0 - 1.0
+    # float64 -> fp16 correctly rounded (numpy's direct conversion; torch goes through float32 and double-rounds): 11 significant
+    # bits for normal numbers, a 2^-24 grid below 2^-14, ties to even -- all exact in float64
+    m, e = torch.frexp(v)
+    q = torch.where(v.abs() >= 2.0 ** -14, torch.ldexp(torch.round(torch.ldexp(m, torch.tensor(11, device=device))), e - 11),
+                    torch.round(v * 2.0 ** 24) * 2.0 ** -24)
+    q = q.to(torch.float32)
+    q[q == 0] = 0.5
+    return q
+
+
+def rmat_torch(scale: int, edge_factor: int = 16, a=0.57, b=0.19, c=0.19, seed: int = 4, device="cuda"):
+    """rmat() above, bit-identical, as torch tensors on `device`: (n, n, row_ptr int32, col_idx int32, vals float32)."""
+    import torch
+    n = 1 << scale
+    ne = edge_factor * n
+    e = torch.arange(ne, dtype=torch.int64, device=device)
+    r = torch.zeros(ne, dtype=torch.int64, device=device)
+    col = torch.zeros(ne, dtype=torch.int64, device=device)
+    for lvl in range(scale):
+        u = _unit_torch(seed + 1000003 * (lvl + 1), e)
+        rbit = u >= (a + b)
+        cbit = ((u >= a) & (u < a + b)) | (u >= a + b + c)
+        r = (r << 1) | rbit
+        col = (col << 1) | cbit
+        del u, rbit, cbit
+    key = torch.unique((r << 32) | col)
+    del r, col, e
+    rows = key >> 32
+    rp = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    rp[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+    return n, n, rp.to(torch.int32), (key & 0xFFFFFFFF).to(torch.int32), values_fp16_torch(seed, key.numel(), device)
+
+
 def x_vector(n: int, seed: int = 1) -> np.ndarray:
     return (_unit(seed ^ 0xABCD, np.arange(n, dtype=np.uint64)) * 2.0 - 1.0).astype(np.float32)

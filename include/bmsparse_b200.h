@@ -169,6 +169,38 @@ int bmsp_partition_block_rows(bmsp_matrix_t A, bmsp_matrix_t Bt, int32_t nparts,
 int bmsp_slice_block_rows(bmsp_matrix_t A, int32_t brow_begin, int32_t brow_end, int32_t rebase_rows,
                           void* stream, bmsp_matrix_t* out);
 
+/* Multi-GPU SpMV with the halo exchange over peer memory (NVLink P2P stores), fused into the product.
+ * Every rank owns a contiguous row range, keeps x for the columns it touches ("extended range") in two
+ * peer-mapped ping-pong buffers and an inbox of epoch flags (bmsp_peer_alloc / bmsp_peer_open).  One step:
+ *   bmsp_spmv_halo(A_local, x_ext[cur], own slice of x_ext[nxt], desc[nxt], e, e + 1, stream)
+ * waits (in the kernel) until every peer published epoch e, computes y, stores the rows each peer needs straight
+ * into that peer's x_ext[nxt] and publishes epoch e + 1.  No NCCL call, no extra launch (row-tiled kernel; the
+ * block-parallel kernel uses a wait and a push kernel around the product). */
+#define BMSP_HALO_MAX 8
+typedef struct {
+    int32_t n_push;                      /* row ranges of my y that some peer needs                          */
+    int32_t push_lo[BMSP_HALO_MAX];      /* local rows [lo, hi), lo a multiple of 4                           */
+    int32_t push_hi[BMSP_HALO_MAX];
+    void* push_dst[BMSP_HALO_MAX];       /* peer-mapped address of row push_lo[i] inside the peer's x buffer  */
+    int32_t n_peer;                      /* peers to signal and to wait for (union of both directions)        */
+    void* peer_flag[BMSP_HALO_MAX];      /* my slot in the peer's inbox (peer-mapped uint32)                  */
+    const void* my_flag[BMSP_HALO_MAX];  /* the peer's slot in my inbox (local uint32)                         */
+    void* scratch;                       /* local device memory, 2 x uint32, zero-initialised                 */
+    int32_t own_col_lo, own_col_hi;      /* columns of x_ext that are this rank's own slice: row tiles whose  */
+                                         /* columns stay inside never wait for a peer                          */
+} bmsp_halo_desc;
+int bmsp_spmv_halo(bmsp_matrix_t A, const float* x_ext, float* y_own, const bmsp_halo_desc* halo,
+                   uint32_t wait_epoch, uint32_t signal_epoch, void* stream);
+/* Push rows of y_own to the peers and publish signal_epoch (first exchange after x is set). */
+int bmsp_halo_push(const float* y_own, int32_t rows, const bmsp_halo_desc* halo, uint32_t signal_epoch, void* stream);
+/* timed_out != 0: a wait gave up after 4 s (a peer died); results since then are invalid. */
+int bmsp_halo_status(const bmsp_halo_desc* halo, void* stream, int32_t* timed_out);
+/* Peer-mapped device memory: allocate + export a 64-byte CUDA IPC handle, open a peer's handle, close, free. */
+int bmsp_peer_alloc(int64_t bytes, void** ptr, void* handle64);
+int bmsp_peer_open(const void* handle64, void** ptr);
+int bmsp_peer_close(void* ptr);
+int bmsp_peer_free(void* ptr);
+
 /* ---- test hook ------------------------------------------------------------------------------- */
 /* Runs the device routine that forms the boolean 8x8 block product (bmp_calculator,
  * SPGEMM.cu:787-810) on n host pairs; used by the parity tests only. */
