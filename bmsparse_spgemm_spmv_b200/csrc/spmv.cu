@@ -18,7 +18,7 @@
 //       load; y is stored as one float4 per thread.  Tiles that exceed the shared-memory capacities are read from
 //       global memory by the same threads.
 //   path 1 "block-parallel" (about one value per block: uniform random, R-MAT)
-//       one warp per work item (a block row, or a 4096-block slice of a long one); lane <-> block,
+//       one warp per work item (a block row, or a 512-block slice of a long one); lane <-> block, 4 x 32 blocks per step,
 //       coalesced 8 B + 4 B metadata loads, value offsets by a warp scan of popc, eight per-row partial
 //       sums per lane kept in shared memory, shuffle reduction at the end; sliced rows are finished by
 //       a deterministic fix-up kernel.
@@ -32,7 +32,7 @@
 
 namespace bmsp {
 
-constexpr int SLICE = 4096;        // blocks per work item (path 1)
+constexpr int SLICE = 512;         // blocks per work item (path 1): 4 steps of 128 blocks; longer block rows are sliced and summed by the fix-up
 
 template <typename X> __device__ __forceinline__ float ld_xp(const X* p);
 template <> __device__ __forceinline__ float ld_xp<float>(const float* p) { return __ldg(p); }
@@ -581,13 +581,18 @@ __global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileAr
 }
 
 // ------------------------------------------------------------------------------------ path 1
-// work item: x = block row, y = first block, z = end block, w = 1 when the block row is sliced
+// work item: x = block row, y = first block, z = end block, w = 1 when the block row is sliced.
+// One warp per item, UNR x 32 blocks per step: every lane issues the metadata loads of its UNR blocks together, the UNR
+// warp scans of popc (value offsets) interleave, and the first value / x element of each of the UNR blocks -- with
+// about one value per block that is nearly all of them -- are loaded back to back before any of them is used, so a
+// step has 4 * UNR independent loads in flight per lane instead of a chain of four dependent ones.
 template <typename T, typename X>
 __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __restrict__ bmps, const int32_t* __restrict__ bcol,
                                                            const uint64_t* __restrict__ offsets, const T* __restrict__ values,
                                                            const int4* __restrict__ work, int n_work, int rows,
                                                            const X* __restrict__ x, float* __restrict__ y,
                                                            float* __restrict__ partial) {
+    constexpr int UNR = 4;
     __shared__ float s_acc[8][8][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int item = blockIdx.x * 8 + wid;
@@ -597,25 +602,52 @@ __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __re
 #pragma unroll
     for (int r = 0; r < 8; r++) acc[r][lane] = 0.f;
     uint64_t vbase = w.y < w.z ? offsets[w.y] : 0;
-    for (int b0 = w.y; b0 < w.z; b0 += 32) {
-        const int b = b0 + lane;
-        const bool valid = b < w.z;
-        uint64_t bmp = valid ? ld_stream_u64(bmps + b) : 0ull;
-        const uint32_t xb = valid ? (uint32_t)ld_stream_s32(bcol + b) * 8u : 0u;
-        const uint32_t cnt = __popcll(bmp);
-        uint32_t inc = cnt;
+    for (int b0 = w.y; b0 < w.z; b0 += 32 * UNR) {
+        uint64_t bmp[UNR]; uint32_t xb[UNR], cnt[UNR], inc[UNR];
+#pragma unroll
+        for (int g = 0; g < UNR; g++) {
+            const int b = b0 + g * 32 + lane;
+            const bool valid = b < w.z;
+            bmp[g] = valid ? ld_stream_u64(bmps + b) : 0ull;
+            xb[g] = valid ? (uint32_t)ld_stream_s32(bcol + b) * 8u : 0u;
+        }
+#pragma unroll
+        for (int g = 0; g < UNR; g++) { cnt[g] = __popcll(bmp[g]); inc[g] = cnt[g]; }
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+#pragma unroll
+            for (int g = 0; g < UNR; g++) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc[g], o);
+                if (lane >= o) inc[g] += t;
+            }
         }
-        uint64_t k = vbase + inc - cnt;
-        vbase += __shfl_sync(0xffffffffu, inc, 31);
-        while (bmp) {
-            const int p = __clzll((long long)bmp);
-            bmp &= ~(0x8000000000000000ull >> p);
-            acc[p >> 3][lane] += val_to_f32(values[k]) * ld_x<X>(x, xb + (uint32_t)(p & 7));
-            k++;
+        uint64_t k[UNR];
+#pragma unroll
+        for (int g = 0; g < UNR; g++) {
+            k[g] = vbase + inc[g] - cnt[g];
+            vbase += __shfl_sync(0xffffffffu, inc[g], 31);
+        }
+        // first value of every block: independent loads, issued together
+        float v0[UNR], x0[UNR]; int p0[UNR];
+#pragma unroll
+        for (int g = 0; g < UNR; g++) {
+            p0[g] = bmp[g] ? __clzll((long long)bmp[g]) : 0;
+            v0[g] = bmp[g] ? val_to_f32(values[k[g]]) : 0.f;
+            x0[g] = bmp[g] ? ld_x<X>(x, xb[g] + (uint32_t)(p0[g] & 7)) : 0.f;
+        }
+#pragma unroll
+        for (int g = 0; g < UNR; g++) {
+            if (bmp[g]) {
+                acc[p0[g] >> 3][lane] += v0[g] * x0[g];
+                uint64_t rem = bmp[g] & ~(0x8000000000000000ull >> p0[g]);
+                uint64_t kk = k[g] + 1;
+                while (rem) {
+                    const int p = __clzll((long long)rem);
+                    rem &= ~(0x8000000000000000ull >> p);
+                    acc[p >> 3][lane] += val_to_f32(values[kk]) * ld_x<X>(x, xb[g] + (uint32_t)(p & 7));
+                    kk++;
+                }
+            }
         }
     }
     float res = 0.f;
@@ -819,7 +851,7 @@ static int host_pipe_get(bmsp_matrix_s* A, cudaStream_t st, HostPipe** out) {
     BMSP_TRY(dev_alloc(&hp->x_dev, (size_t)A->cols * 4 + 256, st));
     BMSP_TRY(dev_alloc_t(&hp->y_dev, (size_t)A->rows + 64, st));
     BMSP_CUDA(cudaStreamCreateWithFlags(&hp->s_cap, cudaStreamNonBlocking));
-    int want = 32;
+    int want = 8;      // P4096 on PCIe 5 x16: 8 chunks 1.67 ms, 16: 1.68, 32: 1.84 (per-chunk dependencies cost more than the shorter fill saves)
     if (const char* e = getenv("BMSP_HOST_CHUNKS")) want = std::max(1, atoi(e));
     if (A->spmv_path == 0 && (int64_t)A->rows * 4 >= (1 << 20)) {
         const int rt = A->tile_rows, ntiles = (int)ceil_div(A->nbr, rt);

@@ -32,3 +32,32 @@ def test_shim_runs_reference_style_main(tmp_path):
     assert "C blocks: 9" in lines and "C nnz: 255" in lines
     assert f"SpMV sum: {sum(g['spmv_ones']):.1f}" in lines
     assert "mmread: 24 24 81 blocks 9" in lines and "CSR C nnz: 255" in lines
+
+
+def test_cli_drivers_print_the_reference_lines(tmp_path):
+    """cli/bmsparse_spgemm_float and cli/bmsparse_spmv_float take the batch scripts' arguments (folder, names without ".mtx",
+    segmented / tc_version / verbose or batched) and print the reference's summary lines (SPGEMM.cu:1278-1285, SPMV.cu:302-306)."""
+    spgemm = os.path.join(ROOT, "cli", "_build", "bmsparse_spgemm_float")
+    spmv = os.path.join(ROOT, "cli", "_build", "bmsparse_spmv_float")
+    if not (os.path.exists(spgemm) and os.path.exists(spmv)):
+        pytest.skip("cli/_build not built")
+    g = load_golden("ragusa16.json")
+    _write_mtx(str(tmp_path / "A_matrix.mtx"), 24, g["A"]["rows"], g["A"]["cols"], g["A"]["vals"])
+    _write_mtx(str(tmp_path / "B_matrix.mtx"), 24, g["B"]["rows"], g["B"]["cols"], g["B"]["vals"])
+    out = subprocess.run([spgemm, str(tmp_path), "A_matrix", "B_matrix", "0", "5", "1"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.splitlines()
+    assert "C blocks: 9" in lines and "C nnz: 255" in lines
+    assert any(l.startswith("bmSparse execution: ") and l.endswith(" μs") for l in lines)
+    assert any(l.startswith("T_7 (numeric): ") for l in lines)
+    assert f"A matrix: {tmp_path}/A_matrix" in lines
+    for args in ([str(tmp_path), "A_matrix", "A_matrix", "0"], [str(tmp_path), "A_matrix"]):
+        out = subprocess.run([spmv] + args, capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stdout + out.stderr
+        lines = out.stdout.splitlines()
+        assert any(l.startswith("bmSparse SpMV execution: ") and l.endswith(" μs") for l in lines)
+        assert f"y checksum: {sum(g['spmv_ones'])}" in lines
+    out = subprocess.run([spgemm, str(tmp_path), "A_matrix"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "MatrixFolder" in out.stdout
+    out = subprocess.run([spgemm, str(tmp_path), "A_matrix", "missing"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 2 and "error" in out.stderr

@@ -60,7 +60,7 @@ def test_poisson_and_generators(B, oracle):
 
 
 def test_long_block_row_is_sliced(B, oracle):
-    """one block row with > 4096 blocks (sliced work items + fix-up) next to empty block rows"""
+    """one block row with far more than 512 blocks (sliced work items + fix-up) next to empty block rows"""
     rng = np.random.default_rng(4)
     nc = 80000
     rows = []

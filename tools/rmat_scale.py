@@ -60,10 +60,12 @@ def main():
         return t.cpu().tolist()
 
     t0 = time.perf_counter()
-    n, _, rp, ci, v = G.rmat(a.scale)
+    n, _, rp_d, ci_d, v_d = G.rmat_torch(a.scale, device=dev)       # bit-identical to generators.rmat (numpy), seconds instead of minutes
+    torch.cuda.synchronize()
     gen_s = time.perf_counter() - t0
     d = lambda x: torch.from_numpy(x).to(dev)
-    A = B.bmSpMatrix.from_csr(n, n, d(rp), d(ci), d(v))
+    A = B.bmSpMatrix.from_csr(n, n, rp_d, ci_d, v_d)
+    rp, ci, v = rp_d.cpu().numpy(), ci_d.cpu().numpy(), v_d.cpu().numpy()
     nbr = A.num_block_rows
     base = {"rows": n, "nnz": int(ci.size), "blocks": A.block_num, "n_gpus": world, "scale": a.scale, "generate_s": round(gen_s, 1)}
 
@@ -102,7 +104,8 @@ def main():
             sh.close()
 
     if "spgemm" in a.what:
-        Bt = B.bmSpMatrix.from_csr(n, n, d(rp), d(ci), d(v), transpose=True)
+        Bt = B.bmSpMatrix.from_csr(n, n, rp_d, ci_d, v_d, transpose=True)
+        del rp_d, ci_d, v_d
         rowlen = np.diff(rp).astype(np.int64)
         flops = 2 * int(rowlen[ci].sum())
         # total candidate pairs -> chunk count; the same partition call splits ranks and chunks
@@ -133,7 +136,7 @@ def main():
             blocks += C.block_num; nnz += C.nnz; cand += info.candidate_pairs; surv += info.surviving_pairs
             if C.block_num:
                 keysum = (keysum + int(C.keys.sum().item())) & ((1 << 62) - 1)
-                valsum += float(C.values.double().sum().item())
+                valsum += float(C.values.sum(dtype=torch.float64).item())
             del C
             done += 1
             if a.max_chunks and done >= a.max_chunks:
