@@ -56,7 +56,7 @@ def test_cli_drivers_print_the_reference_lines(tmp_path):
         assert out.returncode == 0, out.stdout + out.stderr
         lines = out.stdout.splitlines()
         assert any(l.startswith("bmSparse SpMV execution: ") and l.endswith(" μs") for l in lines)
-        assert f"y checksum: {sum(g['spmv_ones'])}" in lines
+        assert f"y checksum: {sum(g['spmv_ones']):g}" in lines
     out = subprocess.run([spgemm, str(tmp_path), "A_matrix"], capture_output=True, text=True, timeout=60)
     assert out.returncode == 1 and "MatrixFolder" in out.stdout
     out = subprocess.run([spgemm, str(tmp_path), "A_matrix", "missing"], capture_output=True, text=True, timeout=60)

@@ -45,6 +45,10 @@ def test_pair_bitmap_kernel(B, oracle):
     a = rng.integers(0, 2**64, n, dtype=np.uint64) & rng.integers(0, 2**64, n, dtype=np.uint64)
     bt = rng.integers(0, 2**64, n, dtype=np.uint64) & rng.integers(0, 2**64, n, dtype=np.uint64) & rng.integers(0, 2**64, n, dtype=np.uint64)
     a[:4] = [0, 2**64 - 1, 1, 2**63]; bt[:4] = [2**64 - 1, 2**64 - 1, 2**63, 1]
+    # sparse A blocks (<= 8 cells) take the per-cell evaluation, the others the row-wise one
+    for i in range(8, n // 2):
+        k = int(rng.integers(1, 9))
+        a[i] = np.bitwise_or.reduce(np.uint64(1) << rng.integers(0, 64, k).astype(np.uint64))
     out = np.empty(n, np.uint64)
     p = lambda x: x.ctypes.data_as(ctypes.c_void_p)
     from bmsparse_spgemm_spmv_b200 import _lib as L
