@@ -39,6 +39,8 @@ struct GemmArgs {
     int32_t cap_words, cap_c, cap_nnz;
     uint32_t* g_bitset; uint32_t* g_wrank; int32_t max_words;   // per-CTA global scratch for over-cap rows
     int32_t* work_counter;
+    const int32_t* row_list;   // when set: the rows to process, in this order (heavy-row / light-row launches); else row_begin + i
+    int32_t n_list;
     uint32_t* row_count;       // COUNT out: C blocks per row (indexed row - row_begin)
     uint32_t* row_surv;        // COUNT out: surviving pairs per row; FILL/NUMERIC in: exclusive scan of it
     uint2* surv_list;          // FILL out / NUMERIC in: (A block, B block) of every surviving pair, row-segmented
@@ -106,7 +108,8 @@ __global__ void pack_meta_kernel(const uint64_t* __restrict__ bmps, const int32_
 __global__ void __launch_bounds__(256) rowinfo_kernel(const int32_t* __restrict__ a_brp, const int32_t* __restrict__ a_bcol,
                                                       const int32_t* __restrict__ b_brp, const int32_t* __restrict__ b_bcol,
                                                       int row_begin, int row_end, int2* __restrict__ rowinfo,
-                                                      unsigned long long* __restrict__ cand, int* __restrict__ maxes) {
+                                                      unsigned long long* __restrict__ cand, int* __restrict__ maxes,
+                                                      unsigned long long* __restrict__ sum_words, unsigned long long* __restrict__ max_cand) {
     const int lane = threadIdx.x & 31;
     const int row = row_begin + blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= row_end) return;
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(256) rowinfo_kernel(const int32_t* __restrict_
         rowinfo[row - row_begin] = make_int2(jbase, words);
         cand[row - row_begin] = c;
         atomicMax(maxes, words);
+        if (words) { atomicAdd(sum_words, (unsigned long long)words); atomicMax(max_cand, c); }
     }
 }
 
@@ -441,8 +445,8 @@ __device__ __forceinline__ void enumerate_row(const GemmArgs& g, const RowCtx& r
     }
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(256) spgemm_pass_kernel(GemmArgs g) {
+template <int PASS, int MAXT>
+__global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = T >> 5;
     // shared-memory carve-up (sizes mirrored by pass_smem_bytes on the host)
@@ -463,7 +467,11 @@ __global__ void __launch_bounds__(256) spgemm_pass_kernel(GemmArgs g) {
     uint2* q = s_queue + wid * QSLOTS;
 
     while (true) {
-        if (tid == 0) { *s_row = g.row_begin + atomicAdd(g.work_counter, 1); *s_cursor = 0; }
+        if (tid == 0) {
+            const int i = atomicAdd(g.work_counter, 1);
+            *s_row = g.row_list ? (i < g.n_list ? g.row_list[i] : g.row_end) : g.row_begin + i;
+            *s_cursor = 0;
+        }
         __syncthreads();
         RowCtx r;
         r.row = *s_row;
@@ -633,20 +641,48 @@ extern "C" int bmsp_debug_pair_bitmap(int64_t n, const uint64_t* a_host, const u
     return BMSP_OK;
 }
 
-template <int PASS>
-static int launch_pass(GemmArgs& g, int T, int sms, cudaStream_t st, int* grid_out) {
+template <int PASS, int MAXT>
+static int launch_pass_t(const GemmArgs& g, int T, int sms, int nrows, cudaStream_t st) {
     const size_t smem = pass_smem_bytes(PASS, T, g.cap_words, g.cap_c, g.cap_nnz);
-    auto kern = spgemm_pass_kernel<PASS>;
+    auto kern = spgemm_pass_kernel<PASS, MAXT>;
     BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
     int occ = 0;
     BMSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
     if (occ < 1) { set_error("spgemm pass %d does not fit: smem %zu", PASS, smem); return BMSP_ERR_CUDA; }
-    int grid = std::min<int64_t>((int64_t)sms * occ, (int64_t)g.row_end - g.row_begin);
+    int grid = (int)std::min<int64_t>((int64_t)sms * occ, (int64_t)nrows);
     grid = std::max(grid, 1);
-    if (grid_out) *grid_out = sms * occ;
     BMSP_CUDA(cudaMemsetAsync(g.work_counter, 0, sizeof(int32_t), st));
     kern<<<grid, T, smem, st>>>(g);
     BMSP_KERNEL_CHECK();
+    return BMSP_OK;
+}
+
+// Heavy block rows (hub rows of power-law inputs: 10^6..10^8 candidate pairs each) are taken out of the row queue and run
+// first, heaviest first, by 1024-thread CTAs on a second stream, while the 256-thread CTAs of the main launch work through the
+// light rows: one CTA per row stays the unit of work, but a hub row gets four times the threads and no longer ends up as the
+// tail of the launch.
+struct RowSplit {
+    bool active = false;
+    int32_t* list = nullptr;       // device: heavy rows (descending weight) then light rows (ascending index)
+    int n_heavy = 0, n_light = 0;
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    size_t heavy_scratch_off = 0;  // words: the heavy launch's slice of g_bitset / g_wrank
+};
+
+template <int PASS>
+static int launch_pass(GemmArgs& g, int T, int sms, cudaStream_t st, const RowSplit& sp) {
+    if (!sp.active) return launch_pass_t<PASS, 256>(g, T, sms, g.row_end - g.row_begin, st);
+    GemmArgs gh = g, gl = g;
+    gh.row_list = sp.list; gh.n_list = sp.n_heavy; gh.work_counter = g.work_counter + 1; gh.G = 32;
+    if (g.g_bitset) { gh.g_bitset = g.g_bitset + sp.heavy_scratch_off; gh.g_wrank = g.g_wrank + sp.heavy_scratch_off; }
+    gl.row_list = sp.list + sp.n_heavy; gl.n_list = sp.n_light;
+    BMSP_CUDA(cudaEventRecord(sp.fork, st));
+    BMSP_CUDA(cudaStreamWaitEvent(sp.side, sp.fork, 0));
+    BMSP_TRY((launch_pass_t<PASS, 1024>(gh, 1024, sms, sp.n_heavy, sp.side)));
+    if (sp.n_light > 0) BMSP_TRY((launch_pass_t<PASS, 256>(gl, T, sms, sp.n_light, st)));
+    BMSP_CUDA(cudaEventRecord(sp.join, sp.side));
+    BMSP_CUDA(cudaStreamWaitEvent(st, sp.join, 0));
     return BMSP_OK;
 }
 
@@ -678,8 +714,13 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     C->rows = A->rows; C->cols = Bt->cols; C->dtype = BMSP_F32; C->transposed = 0;
     C->nbr = (int32_t)ceil_div(C->rows, 8);
     uint32_t *g_bitset = nullptr, *g_wrank = nullptr;
+    RowSplit sp;
     int status = BMSP_OK;
     auto cleanup = [&]() {
+        dev_free(sp.list, st);
+        if (sp.side) { cudaStreamSynchronize(sp.side); cudaStreamDestroy(sp.side); }
+        if (sp.fork) cudaEventDestroy(sp.fork);
+        if (sp.join) cudaEventDestroy(sp.join);
         dev_free(rowinfo, st); dev_free(cand, st); dev_free(small, st); dev_free(row_count, st); dev_free(row_surv, st);
         dev_free(row_nnz, st); dev_free(surv_list, st); dev_free(g_bitset, st); dev_free(g_wrank, st);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -696,15 +737,48 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     SG_TRY(dev_alloc_t(&row_nnz, (size_t)nrows + 2, st));
     SG_CUDA(cudaMemsetAsync(small, 0, 16 * sizeof(int32_t), st));
     int32_t* maxes = small; int32_t* counter = small + 4; unsigned long long* stats = (unsigned long long*)(small + 8);
+    unsigned long long* sum_words = (unsigned long long*)(small + 12);
+    unsigned long long* max_cand = (unsigned long long*)(small + 14);
 
     int32_t h_small[16] = {0};
     if (nrows > 0) {
-        rowinfo_kernel<<<(unsigned)ceil_div(nrows, 8), 256, 0, st>>>(A->brp, A->bcol, Bt->brp, Bt->bcol, rb, re, rowinfo, cand, maxes);
+        rowinfo_kernel<<<(unsigned)ceil_div(nrows, 8), 256, 0, st>>>(A->brp, A->bcol, Bt->brp, Bt->bcol, rb, re, rowinfo, cand, maxes, sum_words, max_cand);
         SG_CUDA(cudaGetLastError());
     }
     SG_CUDA(cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
     const int max_words = h_small[0];
+    unsigned long long h_sum_words = 0;
+    memcpy(&h_sum_words, h_small + 12, sizeof(h_sum_words));
+    // Shared-memory capacities decide how many CTAs an SM holds, and these passes are latency-bound: size them for the rows
+    // that can use them.  When every row fits, take the maxima; when the typical row would not fit anyway (R-MAT: C rows of
+    // 10^4..10^5 blocks spanning every block column), keep the CTAs small -- those rows run from global scratch / global
+    // atomics either way and need the occupancy (R-MAT-17 NUMERIC: 102 KB per CTA = 2 CTAs per SM, 14 % issue utilisation).
+    const double avg_words = nrows ? (double)h_sum_words / nrows : 0.0;
+    unsigned long long h_max_cand = 0;
+    memcpy(&h_max_cand, h_small + 14, sizeof(h_max_cand));
+    {
+        const char* e = getenv("BMSP_SPGEMM_HEAVY");      // candidate pairs that make a row heavy (0 disables the split; tests lower it)
+        const long long heavy_min = e ? atoll(e) : (1ll << 20);
+        if (heavy_min > 0 && nrows > 1 && h_max_cand >= 4ull * (unsigned long long)heavy_min) {
+            std::vector<unsigned long long> hc((size_t)nrows);
+            SG_CUDA(cudaMemcpyAsync(hc.data(), cand, sizeof(unsigned long long) * (size_t)nrows, cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaStreamSynchronize(st));
+            std::vector<int32_t> heavy, order;
+            for (int i = 0; i < nrows; i++) if (hc[i] >= (unsigned long long)heavy_min) heavy.push_back(rb + i);
+            std::sort(heavy.begin(), heavy.end(), [&](int32_t x, int32_t y) { return hc[x - rb] != hc[y - rb] ? hc[x - rb] > hc[y - rb] : x < y; });
+            order = heavy;
+            for (int i = 0; i < nrows; i++) if (hc[i] < (unsigned long long)heavy_min) order.push_back(rb + i);
+            sp.n_heavy = (int)heavy.size(); sp.n_light = nrows - sp.n_heavy;
+            SG_TRY(dev_alloc_t(&sp.list, (size_t)nrows + 1, st));
+            SG_CUDA(cudaMemcpyAsync(sp.list, order.data(), sizeof(int32_t) * (size_t)nrows, cudaMemcpyHostToDevice, st));
+            SG_CUDA(cudaStreamSynchronize(st));       // `order` dies with this scope
+            SG_CUDA(cudaStreamCreateWithFlags(&sp.side, cudaStreamNonBlocking));
+            SG_CUDA(cudaEventCreateWithFlags(&sp.fork, cudaEventDisableTiming));
+            SG_CUDA(cudaEventCreateWithFlags(&sp.join, cudaEventDisableTiming));
+            sp.active = sp.n_heavy > 0;
+        }
+    }
 
     // ---- launch shape from averages: G lanes share one A block, each lane tests 4 B blocks per step
     const double avgB = Bt->nbr ? (double)Bt->nblk / Bt->nbr : 0.0;
@@ -726,14 +800,15 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     g.a_brp = A->brp; g.a_bcol = A->bcol; g.a_bmps = A->bmps; g.a_kmask = A->kmask; g.a_off = A->offsets; g.a_val = (const __half*)A->values;
     g.b_brp = Bt->brp; g.b_bcol = Bt->bcol; g.b_bmps = Bt->bmps; g.b_kmask = Bt->kmask; g.b_off = Bt->offsets; g.b_val = (const __half*)Bt->values;
     g.rowinfo = rowinfo; g.row_begin = rb; g.row_end = re; g.G = G;
-    g.cap_words = std::max(1, std::min(max_words, 8192));
+    g.cap_words = max_words <= 8192 ? std::max(1, max_words) : (avg_words > 4096.0 ? 256 : 8192);
     g.cap_c = 0; g.cap_nnz = 0;
     g.max_words = max_words;
     g.work_counter = counter; g.row_count = row_count; g.row_surv = row_surv; g.row_nnz = row_nnz; g.maxes = maxes; g.stats = stats;
 
     if (max_words > g.cap_words) {
         // over-cap rows use per-CTA global scratch; size it for the largest persistent grid (32 CTAs/SM)
-        const size_t n = (size_t)sms * 32 * max_words;
+        sp.heavy_scratch_off = (size_t)sms * 32 * max_words;                  // + 2 heavy CTAs per SM
+        const size_t n = sp.heavy_scratch_off + (size_t)sms * 2 * max_words;
         SG_TRY(dev_alloc_t(&g_bitset, n, st));
         SG_TRY(dev_alloc_t(&g_wrank, n, st));
         g.g_bitset = g_bitset; g.g_wrank = g_wrank;
@@ -742,7 +817,7 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     // ---- COUNT: C blocks and surviving pairs per block row
     int64_t c_size = 0, n_surv = 0;
     if (nrows > 0) {
-        SG_TRY(launch_pass<PASS_COUNT>(g, T, sms, st, nullptr));
+        SG_TRY(launch_pass<PASS_COUNT>(g, T, sms, st, sp));
         SG_TRY(exclusive_scan_u32(row_count, row_count, nrows, st));
         SG_TRY(exclusive_scan_u32(row_surv, row_surv, nrows, st));
         uint32_t tot[2] = {0, 0};
@@ -774,10 +849,12 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     g.c_off = C->offsets; g.surv_list = surv_list;
 
     // ---- FILL: pair list, keys, bitmaps, row-relative value offsets
-    g.cap_c = std::max(1, std::min(max_c, 4096));
+    const double avg_c = nrows ? (double)c_size / nrows : 0.0;
+    auto clampi = [](double v, int lo, int hi) { return (int)std::min<double>(hi, std::max<double>(lo, v)); };
+    g.cap_c = max_c <= 4096 ? std::max(1, max_c) : (avg_c <= 512.0 ? clampi(4.0 * avg_c, 256, 2048) : 64);
     if (c_size > 0) {
         if (max_c > g.cap_c) SG_CUDA(cudaMemsetAsync(C->bmps, 0, sizeof(uint64_t) * c_size, st));
-        SG_TRY(launch_pass<PASS_FILL>(g, T, sms, st, nullptr));
+        SG_TRY(launch_pass<PASS_FILL>(g, T, sms, st, sp));
     } else if (nrows > 0) {
         SG_CUDA(cudaMemsetAsync(row_nnz, 0, sizeof(uint64_t) * ((size_t)nrows + 1), st));
     }
@@ -801,11 +878,14 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
         if (path == 1) {
             g.cap_c = std::max(1, std::min(max_c, 192));
             if (max_c > g.cap_c) SG_CUDA(cudaMemsetAsync(C->values, 0, (size_t)c_nnz * 4, st));
-            SG_TRY(launch_pass<PASS_NUMERIC_MMA>(g, 32, sms, st, nullptr));
+            SG_TRY((launch_pass_t<PASS_NUMERIC_MMA, 256>(g, 32, sms, nrows, st)));
         } else {
-            g.cap_nnz = std::max(1, std::min(max_rownnz, 12288));
+            const double avg_nnz = nrows ? (double)c_nnz / nrows : 0.0;
+            if (max_c <= 4096 && max_rownnz <= 12288) { g.cap_c = std::max(1, max_c); g.cap_nnz = std::max(1, max_rownnz); }
+            else if (avg_c <= 512.0 && avg_nnz <= 1536.0) { g.cap_c = clampi(4.0 * avg_c, 256, 2048); g.cap_nnz = clampi(4.0 * avg_nnz, 1024, 8192); }
+            else { g.cap_c = 64; g.cap_nnz = 256; }
             if (max_c > g.cap_c || max_rownnz > g.cap_nnz) SG_CUDA(cudaMemsetAsync(C->values, 0, (size_t)c_nnz * 4, st));
-            SG_TRY(launch_pass<PASS_NUMERIC>(g, T, sms, st, nullptr));
+            SG_TRY(launch_pass<PASS_NUMERIC>(g, T, sms, st, sp));
         }
     }
     finish_rows_kernel<<<(unsigned)ceil_div(C->nbr + 1, 256), 256, 0, st>>>(row_count, row_nnz, rb, re, C->nbr, C->brp, C->rvb, C->offsets, c_size, c_nnz);

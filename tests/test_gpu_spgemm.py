@@ -140,3 +140,20 @@ def test_chained_product_via_block_transpose(B, oracle):
     S = sp.csr_matrix((v, ci, rp), shape=(nr, nc)); R = (S @ S @ S).tocoo()
     a, b, mean, mx = C2.compare(R.row, R.col, R.data)
     assert (a, b) == (0, 0) and mx == 0.0      # integers up to 6*4^2.. exact in fp16/fp32
+
+
+def test_heavy_row_split(B, oracle, monkeypatch):
+    """hub rows run in their own launch (1024-thread CTAs on a side stream, heaviest first): same structure bit for bit,
+    values within the fp32-accumulation tolerance.  The threshold is lowered so that small inputs exercise the split."""
+    G = B.generators
+    monkeypatch.setenv("BMSP_SPGEMM_HEAVY", "300")
+    for gen in (lambda: G.rmat(11), lambda: G.uniform_random(3000, 16), lambda: G.poisson5pt(40, 40)):
+        nr, nc, rp, ci, v = gen()
+        C, info, exp = _mult_check(B, oracle, (nr, nc), (rp, ci, v), (nr, nc), (rp, ci, v))
+        # sharded range with the split active
+        A = B.bmSpMatrix.from_csr(nr, nc, rp, ci, v); Bt = B.bmSpMatrix.from_csr(nr, nc, rp, ci, v, transpose=True)
+        nbr = A.num_block_rows
+        C2, _ = B.bmSparse_mult(A, Bt, brow_range=(nbr // 3, nbr))
+        k, b, o, vals = C.download(); k2, b2, o2, vals2 = C2.download()
+        first = int(np.searchsorted(k >> np.uint64(32), nbr // 3))
+        assert np.array_equal(k[first:], k2) and np.array_equal(b[first:], b2)

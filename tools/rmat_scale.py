@@ -10,7 +10,7 @@ SpMV   rows split by SpMV bytes (bmsp_partition_block_rows); every rank keeps x 
        the exchange is an all-gather written by the producers).  value = algorithmic bytes of the WHOLE matrix /
        max-over-ranks device time per product.
 SpGEMM A's block rows split by candidate pairs; B^t replicated; every rank multiplies its rows in chunks of
-       <= --chunk-pairs candidate pairs (the scale-22 product, ~7e10 values, fits no GPU: each chunk's C is reduced
+       <= --chunk-pairs candidate pairs (default 3e9; the scale-22 product, ~7e10 values, fits no GPU: each chunk's C is reduced
        to a checksum -- blocks, values, sum of keys, sum of values -- and dropped).  The checksums are summed over
        ranks and are independent of N.  value = 2 * scalar products / max-over-ranks time of the bmsp_spgemm calls.
 Prints one JSON line per operator (rank 0)."""
@@ -37,7 +37,7 @@ def main():
     ap.add_argument("--scale", type=int, default=22)
     ap.add_argument("--what", default="spmv,spgemm")
     ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--chunk-pairs", type=float, default=3e8)
+    ap.add_argument("--chunk-pairs", type=float, default=3e9, help="candidate pairs per bmsp_spgemm call: large enough that a chunk holds many block rows next to its hub rows (3e8: RM20 11.6 s; one call for all of RM18 is 4x faster than 12 chunks), small enough that C stays below 2^31 blocks / 2^32 values and fits HBM")
     ap.add_argument("--max-chunks", type=int, default=0, help="stop the SpGEMM after this many chunks per rank (0 = all): bounded sample")
     ap.add_argument("--halo", default="auto")
     a = ap.parse_args()
