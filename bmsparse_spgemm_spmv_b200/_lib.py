@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbmsparse_b200.so")
+LIB_PATH = os.environ.get("BMSP_LIB_PATH") or os.path.join(_HERE, "lib", "libbmsparse_b200.so")   # override: A/B runs of two builds
 
 F16, F32 = 0, 1
 HOST, DEVICE = 0, 1

@@ -108,11 +108,7 @@ constexpr int XL_STRIDE = 33;      // staged x line pitch, elements (32 + 1 skew
 constexpr int PLAN_MAXB = 2048;    // blocks per tile the planner sorts in shared memory
 constexpr int XL_MAX = 1900;       // distinct lines per tile (16-bit element offsets)
 
-// 64 bytes.  [lmin, lmax] = x lines touched.  When the tile's distinct lines form at most three runs of consecutive lines
-// (stencils: the rows above, the tile's own rows, the rows below; bands: one run) flags bit 2 is set and the runs are stored
-// here, so the kernel derives every line index from the descriptor instead of loading the line list -- one dependent global
-// round trip less between the descriptor and the x loads.
-struct __align__(16) TileDesc { int32_t p0, nb; uint32_t v0; int32_t nv, nl, flags, lmin, lmax; int32_t rs0, rs1, rs2, rc0, rc1, pad0, pad1, pad2; };
+struct __align__(16) TileDesc { int32_t p0, nb; uint32_t v0; int32_t nv, nl, flags, lmin, lmax; };   // 32 bytes; [lmin, lmax] = x lines touched
 
 __global__ void __launch_bounds__(256) tile_plan_kernel(const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
                                                         const uint32_t* __restrict__ rvb, int nbr, int ncols, int rt, TileDesc* __restrict__ desc,
@@ -127,7 +123,6 @@ __global__ void __launch_bounds__(256) tile_plan_kernel(const int32_t* __restric
     const uint32_t v0 = rvb[r0], v1 = rvb[r1];
     TileDesc d;
     d.p0 = p0; d.nb = nb; d.v0 = v0; d.nv = (int32_t)(v1 - v0); d.nl = 0; d.flags = 0; d.lmin = 0; d.lmax = nb > 0 ? 0x7FFFFFFF : -1;
-    d.rs0 = d.rs1 = d.rs2 = d.rc0 = d.rc1 = d.pad0 = d.pad1 = d.pad2 = 0;
     if (nb > PLAN_MAXB) {          // too many blocks to plan: the kernel reads this tile straight from global memory
         if (tid == 0) { desc[t] = d; atomicAdd(stats + 4, 1ull); }
         return;
@@ -185,18 +180,8 @@ __global__ void __launch_bounds__(256) tile_plan_kernel(const int32_t* __restric
         }
     if (tid == 0) {
         // flags: bit 0 = planned (x offsets valid), bit 1 = the last line reaches past the last column (guarded gather)
-        int runs = 0;
-        if (nb > 0) {
-            d.lmin = (int32_t)s_uniq[0]; d.lmax = (int32_t)s_uniq[nl - 1];
-            // runs of consecutive lines (gives up at the fourth)
-            int rs[3] = {0, 0, 0}, rc[3] = {0, 0, 0};
-            for (int j = 0; j < nl && runs <= 3; j++) {
-                if (j == 0 || s_uniq[j] != s_uniq[j - 1] + 1u) { if (++runs <= 3) { rs[runs - 1] = (int)s_uniq[j]; rc[runs - 1] = 1; } }
-                else rc[runs - 1]++;
-            }
-            if (runs <= 3) { d.rs0 = rs[0]; d.rs1 = rs[1]; d.rs2 = rs[2]; d.rc0 = rc[0]; d.rc1 = rc[1]; }
-        }
-        d.nl = nl; d.flags = (nb > 0 && runs <= 3 ? 4 : 0) | (ok ? 1 : 0) | ((nl > 0 && (uint64_t)s_uniq[nl - 1] * 32u + 32u > (uint64_t)ncols) ? 2 : 0);
+        if (nb > 0) { d.lmin = (int32_t)s_uniq[0]; d.lmax = (int32_t)s_uniq[nl - 1]; }
+        d.nl = nl; d.flags = (ok ? 1 : 0) | ((nl > 0 && (uint64_t)s_uniq[nl - 1] * 32u + 32u > (uint64_t)ncols) ? 2 : 0);
         desc[t] = d;
         atomicMax(stats + 0, (unsigned long long)nb);
         atomicMax(stats + 1, (unsigned long long)(v1 - v0));
@@ -478,12 +463,8 @@ __global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileAr
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + a.so.bar);
 
     const int4* dp = reinterpret_cast<const int4*>(a.desc + t);
-    // the CTA that will take over this slot (about one resident wave later) starts with a descriptor that is already in L2
-    if (tid == 32) { const int tn = t + 2048; if (tn * RTT < a.nbr) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.desc + tn)); }
     const int4 d0 = __ldg(dp);
     const int4 d1 = __ldg(dp + 1);       // nl, flags, lmin, lmax
-    const int4 d2 = __ldg(dp + 2);       // rs0, rs1, rs2, rc0
-    const int rc1 = __ldg(reinterpret_cast<const int*>(dp + 3));
     const int p0 = d0.x, nb = d0.y, nv = d0.w, nl = d1.x;
     const uint32_t v0 = (uint32_t)d0.z, v0a = v0 & ~(uint32_t)(VA - 1);
     const bool staged = (d1.y & 1) && nb <= a.cap_blk && nv <= a.cap_val && nl <= a.cap_lines;
@@ -521,22 +502,12 @@ __global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileAr
         const uint32_t* lp = a.lines + p0 + l0;
         uint32_t dst = sbase + a.so.xs + ((uint32_t)l0 * XL_STRIDE + j4) * SX;
         const X* xj = x + j4;
-        const bool runs = d1.y & 4;
-        // line index of the tile's l-th distinct line: from the descriptor's runs, else from the line list
-        auto line_of = [&](int l, const uint32_t* lpl) -> uint32_t {
-            if (runs) {
-                if (l < d2.w) return (uint32_t)(d2.x + l);
-                l -= d2.w;
-                return (uint32_t)(l < rc1 ? d2.y + l : d2.z + (l - rc1));
-            }
-            return __ldg(lpl);
-        };
         if (!(d1.y & 2)) {
             for (int l = l0; l < nl; l += LPI * GB) {
                 XQuad<X> buf[GB];
 #pragma unroll
                 for (int g = 0; g < GB; g++)
-                    if (l + g * LPI < nl) buf[g] = *reinterpret_cast<const XQuad<X>*>(xj + (size_t)line_of(l + g * LPI, lp + g * LPI) * 32u);
+                    if (l + g * LPI < nl) buf[g] = *reinterpret_cast<const XQuad<X>*>(xj + (size_t)__ldg(lp + g * LPI) * 32u);
 #pragma unroll
                 for (int g = 0; g < GB; g++)
                     if (l + g * LPI < nl) {
@@ -548,7 +519,7 @@ __global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileAr
             }
         } else {      // the tile's last line reaches past the last column: element-wise guarded loads
             for (int l = l0; l < nl; l += LPI) {
-                const uint32_t col = line_of(l, lp) * 32u + j4;
+                const uint32_t col = __ldg(lp) * 32u + j4;
 #pragma unroll
                 for (int e = 0; e < 4; e++) sts_x<X>(dst + e * SX, col + e < (uint32_t)a.cols ? x[col + e] : X(0.f));
                 lp += LPI;
