@@ -586,18 +586,27 @@ __global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileAr
 // warp scans of popc (value offsets) interleave, and the first value / x element of each of the UNR blocks -- with
 // about one value per block that is nearly all of them -- are loaded back to back before any of them is used, so a
 // step has 4 * UNR independent loads in flight per lane instead of a chain of four dependent ones.
-template <typename T, typename X>
+// H = HaloDev: the multi-GPU variant -- every CTA waits for the peers' x slices before its first gather, every finished row
+// is stored to the peers that need it (for a scattered matrix: all of them -- an all-gather written by the producers, spread
+// over the whole kernel instead of a copy pass after it), and the last CTA publishes the epoch unless a fix-up kernel follows.
+template <typename T, typename X, typename H = NoHalo>
 __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __restrict__ bmps, const int32_t* __restrict__ bcol,
                                                            const uint64_t* __restrict__ offsets, const T* __restrict__ values,
                                                            const int4* __restrict__ work, int n_work, int rows,
                                                            const X* __restrict__ x, float* __restrict__ y,
-                                                           float* __restrict__ partial) {
+                                                           float* __restrict__ partial, const H hd) {
+    constexpr bool DIST = !std::is_same<H, NoHalo>::value;
     constexpr int UNR = 4;
     __shared__ float s_acc[8][8][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int item = blockIdx.x * 8 + wid;
-    if (item >= n_work) return;
-    const int4 w = work[item];
+    if constexpr (DIST) {
+        if ((int)threadIdx.x < hd.n_peer) halo_wait(hd, threadIdx.x);
+        __syncthreads();
+    }
+    const bool active = item < n_work;
+    if (!DIST && !active) return;
+    const int4 w = active ? work[item] : make_int4(0, 0, 0, 0);      // (multi-GPU variant: idle warps stay for the barrier below)
     float (*acc)[32] = s_acc[wid];
 #pragma unroll
     for (int r = 0; r < 8; r++) acc[r][lane] = 0.f;
@@ -658,26 +667,52 @@ __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __re
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == r) res = v;
     }
-    if (lane < 8) {
+    if (lane < 8 && active) {
         if (w.w) partial[(int64_t)item * 8 + lane] = res;
         else {
             const int64_t row = (int64_t)w.x * 8 + lane;
-            if (row < rows) y[row] = res;
+            if (row < rows) {
+                y[row] = res;
+                if constexpr (DIST) {
+                    for (int i = 0; i < hd.n_push; i++)
+                        if (row >= hd.lo[i] && row < hd.hi[i]) hd.dst[i][row - hd.lo[i]] = res;
+                }
+            }
+        }
+    }
+    if constexpr (DIST) {
+        if (hd.n_sig) {          // no fix-up kernel after this one: this launch publishes the epoch
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) halo_signal(hd);
         }
     }
 }
 
 // sliced block rows: sum the slices' partials in slice order (deterministic), one thread per matrix row
+template <typename H = NoHalo>
 __global__ void spmv_fixup_kernel(const int32_t* __restrict__ item_ofs, const float* __restrict__ partial, int nbr, int rows,
-                                  float* __restrict__ y) {
+                                  float* __restrict__ y, const H hd) {
+    constexpr bool DIST = !std::is_same<H, NoHalo>::value;
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= rows) return;
-    const int br = (int)(row >> 3), r = (int)(row & 7);
-    const int i0 = item_ofs[br], i1 = item_ofs[br + 1];
-    if (i1 - i0 <= 1) return;
-    float s = 0.f;
-    for (int i = i0; i < i1; i++) s += partial[(int64_t)i * 8 + r];
-    y[row] = s;
+    if (row < rows) {
+        const int br = (int)(row >> 3), r = (int)(row & 7);
+        const int i0 = item_ofs[br], i1 = item_ofs[br + 1];
+        if (i1 - i0 > 1) {
+            float s = 0.f;
+            for (int i = i0; i < i1; i++) s += partial[(int64_t)i * 8 + r];
+            y[row] = s;
+            if constexpr (DIST) {
+                for (int i = 0; i < hd.n_push; i++)
+                    if (row >= hd.lo[i] && row < hd.hi[i]) hd.dst[i][row - hd.lo[i]] = s;
+            }
+        }
+    }
+    if constexpr (DIST) {        // the last kernel of the product: publish the epoch
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) halo_signal(hd);
+    }
 }
 
 __global__ void work_count_kernel(const int32_t* __restrict__ brp, int nbr, uint32_t* __restrict__ cnt) {
@@ -711,6 +746,7 @@ static int plan_tiles(bmsp_matrix_s* m, cudaStream_t st) {
     int rt = 64;
     const double row_bytes = ((double)m->nblk * (8 + 2 + 16) + (double)m->nnz * vsize) / m->nbr + 8;
     while (rt > 16 && row_bytes * rt > 20.0 * 1024) rt >>= 1;
+    if (const char* e = getenv("BMSP_SPMV_RT")) { const int v = atoi(e); if (v == 16 || v == 32 || v == 64 || v == 128) rt = v; }   // experiments
     m->tile_rows = rt;
     const int ntiles = (int)ceil_div(m->nbr, rt);
     unsigned long long* stats = nullptr;
@@ -799,6 +835,7 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, 
         if (grid <= 0) return BMSP_OK;
         // default: one thread per bitmap half; BMSP_SPMV_VARIANT=1: one thread per block row (64-row tiles only).
         // Measured on P4096: 92.7 us vs 103.5 us (fewer instructions, but too few warps to hide the staging latency).
+        if (rt == 128) return launch_tile_kernel<T, X, 128, 2, 6, H>(a, x, y, hd, grid, smem, st);
         if (rt == 32) return launch_tile_kernel<T, X, 32, 2, 24, H>(a, x, y, hd, grid, smem, st);
         if (rt == 16) return launch_tile_kernel<T, X, 16, 2, 32, H>(a, x, y, hd, grid, smem, st);
         if constexpr (std::is_same<H, NoHalo>::value) {
@@ -807,12 +844,17 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, 
         }
         return launch_tile_kernel<T, X, 64, 2, 12, H>(a, x, y, hd, grid, smem, st);
     }
-    spmv_blockpar_kernel<T, X><<<(unsigned)ceil_div(A->n_work, 8), 256, 0, st>>>(A->bmps, A->bcol, A->offsets, (const T*)A->values,
-                                                                               (const int4*)A->work, A->n_work, A->rows, x, y,
-                                                                               A->split_partial);
+    const unsigned grid1 = (unsigned)ceil_div(A->n_work, 8), grid2 = (unsigned)ceil_div(A->rows, 256);
+    H h1 = hd, h2 = hd;
+    if constexpr (!std::is_same<H, NoHalo>::value) {
+        h1.n_sig = A->n_split > 0 ? 0u : grid1;     // the epoch is published by the product's last kernel
+        h2.n_sig = grid2;
+    }
+    spmv_blockpar_kernel<T, X, H><<<grid1, 256, 0, st>>>(A->bmps, A->bcol, A->offsets, (const T*)A->values, (const int4*)A->work, A->n_work,
+                                                       A->rows, x, y, A->split_partial, h1);
     BMSP_KERNEL_CHECK();
     if (A->n_split > 0) {
-        spmv_fixup_kernel<<<(unsigned)ceil_div(A->rows, 256), 256, 0, st>>>(A->split_rows, A->split_partial, A->nbr, A->rows, y);
+        spmv_fixup_kernel<H><<<grid2, 256, 0, st>>>(A->split_rows, A->split_partial, A->nbr, A->rows, y, h2);
         BMSP_KERNEL_CHECK();
     }
     return BMSP_OK;
@@ -1078,7 +1120,10 @@ extern "C" int bmsp_spmv_halo(bmsp_matrix_t A, const float* x_ext, float* y_own,
         return A->dtype == BMSP_F16 ? launch_spmv<__half, float, HaloDev>(A, x_ext, y_own, st, 0, -1, h)
                                     : launch_spmv<float, float, HaloDev>(A, x_ext, y_own, st, 0, -1, h);
     }
-    // block-parallel path (or BMSP_HALO_FUSED=0): wait kernel, product, push kernel
+    if (A->spmv_path == 1 && fused)
+        return A->dtype == BMSP_F16 ? launch_spmv<__half, float, HaloDev>(A, x_ext, y_own, st, 0, -1, h)
+                                    : launch_spmv<float, float, HaloDev>(A, x_ext, y_own, st, 0, -1, h);
+    // BMSP_HALO_FUSED=0: wait kernel, product, push kernel
     halo_wait_kernel<<<1, 32, 0, st>>>(h);
     BMSP_KERNEL_CHECK();
     BMSP_TRY(bmsp_spmv(A, x_ext, BMSP_F32, y_own, stream));

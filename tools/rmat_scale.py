@@ -9,7 +9,7 @@ SpMV   rows split by SpMV bytes (bmsp_partition_block_rows); every rank keeps x 
        peers' slices arrive over NVLink peer memory (bmsp_spmv_halo; for R-MAT every rank needs every slice, so
        the exchange is an all-gather written by the producers).  value = algorithmic bytes of the WHOLE matrix /
        max-over-ranks device time per product.
-SpGEMM A's block rows split by candidate pairs; B^t replicated; every rank multiplies its rows in chunks of
+SpGEMM A's block rows split by candidate pairs into N x k chunks dealt to the ranks block-cyclically; B^t replicated; chunks of
        <= --chunk-pairs candidate pairs (default 3e9; the scale-22 product, ~7e10 values, fits no GPU: each chunk's C is reduced
        to a checksum -- blocks, values, sum of keys, sum of values -- and dropped).  The checksums are summed over
        ranks and are independent of N.  value = 2 * scalar products / max-over-ranks time of the bmsp_spgemm calls.
@@ -114,7 +114,9 @@ def main():
         cand_total = int(blen[bcol].sum())
         cpr = max(1, int(np.ceil(cand_total / world / a.chunk_pairs)))
         bounds = A.partition_block_rows(world * cpr, Bt)
-        mine = range(rank * cpr, (rank + 1) * cpr)
+        # block-cyclic: rank r multiplies chunks r, r + N, r + 2N, ... -- the hub rows sit in the first chunks, and a hub chunk costs
+        # more per candidate pair than a tail chunk, so contiguous ranges would leave rank 0 with the slowest ones
+        mine = range(rank, world * cpr, world)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
