@@ -427,6 +427,14 @@ __device__ __forceinline__ void halo_store(const HaloDev& h, int row, int rows, 
 __global__ void halo_wait_kernel(const HaloDev h) {
     if ((int)threadIdx.x < h.n_peer) halo_wait(h, threadIdx.x);
 }
+// publishes the epoch after a product whose kernels stored the peers' rows without fences of their own: the kernel boundary
+// orders those stores before this thread, its system fence and release stores carry them to the peers
+__global__ void halo_flag_kernel(const HaloDev h) {
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int p = 0; p < h.n_peer; p++) st_release_sys(h.peer_flag[p], h.signal_epoch);
+    }
+}
 // stand-alone push (first exchange after set_x, and products that run the block-parallel kernel)
 __global__ void __launch_bounds__(256) halo_push_kernel(const float* __restrict__ y, const HaloDev h) {
     for (int i = 0; i < h.n_push; i++) {
@@ -586,9 +594,11 @@ __global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileAr
 // warp scans of popc (value offsets) interleave, and the first value / x element of each of the UNR blocks -- with
 // about one value per block that is nearly all of them -- are loaded back to back before any of them is used, so a
 // step has 4 * UNR independent loads in flight per lane instead of a chain of four dependent ones.
-// H = HaloDev: the multi-GPU variant -- every CTA waits for the peers' x slices before its first gather, every finished row
-// is stored to the peers that need it (for a scattered matrix: all of them -- an all-gather written by the producers, spread
-// over the whole kernel instead of a copy pass after it), and the last CTA publishes the epoch unless a fix-up kernel follows.
+// H = HaloDev: the multi-GPU variant -- every finished row is stored to the peers that need it (for a scattered matrix: all of
+// them -- an all-gather written by the producers, spread over the whole kernel instead of a copy pass after it).  The wait
+// for the peers' epoch and the publication of this one are one-thread kernels around the product, not per-CTA code: a system
+// fence invalidates the SM's whole L1 (SASS: MEMBAR.SYS + CCTL.IVALL), and this kernel lives on L1 hits of its x gathers --
+// with a fence at the start and the end of every CTA the 2-GPU R-MAT-22 product took 1161 us against 600 us on one GPU.
 template <typename T, typename X, typename H = NoHalo>
 __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __restrict__ bmps, const int32_t* __restrict__ bcol,
                                                            const uint64_t* __restrict__ offsets, const T* __restrict__ values,
@@ -600,13 +610,9 @@ __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __re
     __shared__ float s_acc[8][8][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int item = blockIdx.x * 8 + wid;
-    if constexpr (DIST) {
-        if ((int)threadIdx.x < hd.n_peer) halo_wait(hd, threadIdx.x);
-        __syncthreads();
-    }
-    const bool active = item < n_work;
-    if (!DIST && !active) return;
-    const int4 w = active ? work[item] : make_int4(0, 0, 0, 0);      // (multi-GPU variant: idle warps stay for the barrier below)
+    if (item >= n_work) return;
+    const bool active = true;
+    const int4 w = work[item];
     float (*acc)[32] = s_acc[wid];
 #pragma unroll
     for (int r = 0; r < 8; r++) acc[r][lane] = 0.f;
@@ -680,20 +686,13 @@ __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __re
             }
         }
     }
-    if constexpr (DIST) {
-        if (hd.n_sig) {          // no fix-up kernel after this one: this launch publishes the epoch
-            __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x == 0) halo_signal(hd);
-        }
-    }
 }
 
 // sliced block rows: sum the slices' partials in slice order (deterministic), one thread per matrix row
 template <typename H = NoHalo>
 __global__ void spmv_fixup_kernel(const int32_t* __restrict__ item_ofs, const float* __restrict__ partial, int nbr, int rows,
                                   float* __restrict__ y, const H hd) {
-    constexpr bool DIST = !std::is_same<H, NoHalo>::value;
+    constexpr bool DIST = !std::is_same<H, NoHalo>::value;     // multi-GPU variant: the finished rows also go to the peers
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row < rows) {
         const int br = (int)(row >> 3), r = (int)(row & 7);
@@ -707,11 +706,6 @@ __global__ void spmv_fixup_kernel(const int32_t* __restrict__ item_ofs, const fl
                     if (row >= hd.lo[i] && row < hd.hi[i]) hd.dst[i][row - hd.lo[i]] = s;
             }
         }
-    }
-    if constexpr (DIST) {        // the last kernel of the product: publish the epoch
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) halo_signal(hd);
     }
 }
 
@@ -845,18 +839,16 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, 
         return launch_tile_kernel<T, X, 64, 2, 12, H>(a, x, y, hd, grid, smem, st);
     }
     const unsigned grid1 = (unsigned)ceil_div(A->n_work, 8), grid2 = (unsigned)ceil_div(A->rows, 256);
-    H h1 = hd, h2 = hd;
-    if constexpr (!std::is_same<H, NoHalo>::value) {
-        h1.n_sig = A->n_split > 0 ? 0u : grid1;     // the epoch is published by the product's last kernel
-        h2.n_sig = grid2;
-    }
+    constexpr bool DIST = !std::is_same<H, NoHalo>::value;
+    if constexpr (DIST) { halo_wait_kernel<<<1, 32, 0, st>>>(hd); BMSP_KERNEL_CHECK(); }
     spmv_blockpar_kernel<T, X, H><<<grid1, 256, 0, st>>>(A->bmps, A->bcol, A->offsets, (const T*)A->values, (const int4*)A->work, A->n_work,
-                                                       A->rows, x, y, A->split_partial, h1);
+                                                       A->rows, x, y, A->split_partial, hd);
     BMSP_KERNEL_CHECK();
     if (A->n_split > 0) {
-        spmv_fixup_kernel<H><<<grid2, 256, 0, st>>>(A->split_rows, A->split_partial, A->nbr, A->rows, y, h2);
+        spmv_fixup_kernel<H><<<grid2, 256, 0, st>>>(A->split_rows, A->split_partial, A->nbr, A->rows, y, hd);
         BMSP_KERNEL_CHECK();
     }
+    if constexpr (DIST) { halo_flag_kernel<<<1, 32, 0, st>>>(hd); BMSP_KERNEL_CHECK(); }
     return BMSP_OK;
 }
 

@@ -157,3 +157,44 @@ def test_heavy_row_split(B, oracle, monkeypatch):
         k, b, o, vals = C.download(); k2, b2, o2, vals2 = C2.download()
         first = int(np.searchsorted(k >> np.uint64(32), nbr // 3))
         assert np.array_equal(k[first:], k2) and np.array_equal(b[first:], b2)
+
+
+def test_full_size_u1m_properties(B):
+    """BASELINE config 3 at full size (uniform-random 1M x 1M, 16 nnz/row, A*A): size-independent properties.
+    (i) the structure counts the reference's own CUDA operator produced on the same input (profiles/r1_compare_baselines.json);
+    (ii) sum of all C entries = (1^T A)(A 1), evaluated in fp64 from A alone;  (iii) C x = A (A x) with both sides through the
+    SpMV kernels (C is an fp32 bmSparse matrix, A fp16) -- ties the two operators together;  (iv) keys strictly ascending and
+    offsets = exclusive scan of popcount(bitmaps)."""
+    G = B.generators
+    nr, nc, rp, ci, v = G.uniform_random(1_000_000, 16, seed=2)
+    d = lambda a: torch.from_numpy(a).cuda()
+    A = B.bmSpMatrix.from_csr(nr, nc, d(rp), d(ci), d(v)); Bt = B.bmSpMatrix.from_csr(nr, nc, d(rp), d(ci), d(v), transpose=True)
+    C, info = B.bmSparse_mult(A, Bt)
+    assert (C.block_num, C.nnz) == (253900089, 255969153)
+    assert info.candidate_pairs == 2045965407 and info.surviving_pairs == 255971715
+    # (ii)
+    v64 = v.astype(np.float64)
+    rowsum = np.add.reduceat(v64, rp[:-1].astype(np.int64))
+    colsum = np.bincount(ci, weights=v64, minlength=nc)
+    exact = float(colsum @ rowsum)
+    scale = float(np.bincount(ci, weights=np.abs(v64), minlength=nc) @ np.add.reduceat(np.abs(v64), rp[:-1].astype(np.int64)))
+    got = float(C.values.sum(dtype=torch.float64).item())
+    assert abs(got - exact) <= 1e-6 * scale, (got, exact, scale)
+    # (iv)
+    k = C.keys
+    assert bool((k[1:] > k[:-1]).all())
+    bm = C.bmps
+    pc = torch.zeros_like(bm)
+    t = bm.clone()
+    for _ in range(64):          # popcount of int64 bit patterns without uint64 support
+        pc += t & 1
+        t = (t >> 1) & 0x7FFFFFFFFFFFFFFF
+    off = C.offsets
+    assert int(off[0]) == 0 and int(off[-1]) == C.nnz and torch.equal(off[1:] - off[:-1], pc)
+    del pc, t
+    # (iii)
+    x = d(G.x_vector(nc))
+    y1 = B.bmSparse_SpMV(A, B.bmSparse_SpMV(A, x))
+    y2 = B.bmSparse_SpMV(C, x)
+    tol = 1e-4 * float(y1.abs().max())
+    assert float((y1 - y2).abs().max()) <= tol

@@ -93,9 +93,21 @@ def main():
             step()
         e1.record(); e1.synchronize()
         ms = allmax(e0.elapsed_time(e1) / a.steps)
+        local = None
         if sh is not None:
             sh.check()
-        line = dict(base, op="spmv", metric="SpMV HBM GB/s", value=nbytes / ms / 1e6, ms_per_step=ms, algorithmic_bytes=nbytes,
+            # per-rank diagnostics: the local product alone (no exchange), rows and blocks of the shard
+            xl = sh.x[sh.cur]; yl = torch.empty(sh.own_hi - sh.own_lo, device=dev)
+            for _ in range(3):
+                B.bmSparse_SpMV(sh.local, xl, yl)
+            e0.record()
+            for _ in range(a.steps):
+                B.bmSparse_SpMV(sh.local, xl, yl)
+            e1.record(); e1.synchronize()
+            mine = {"rank": rank, "local_ms": round(e0.elapsed_time(e1) / a.steps, 4), "rows": sh.own_hi - sh.own_lo, "blocks": sh.local.block_num}
+            local = [None] * world
+            dist.all_gather_object(local, mine)
+        line = dict(base, op="spmv", per_rank=local, metric="SpMV HBM GB/s", value=nbytes / ms / 1e6, ms_per_step=ms, algorithmic_bytes=nbytes,
                     halo=("peer-memory" if sh is not None and sh.p2p is not None else ("nccl" if sh is not None else "none")),
                     halo_bytes_in_per_rank=(sh.halo_bytes if sh is not None else 0), scaling="strong")
         if rank == 0:
