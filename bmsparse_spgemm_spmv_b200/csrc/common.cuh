@@ -40,6 +40,8 @@ struct bmsp_matrix_s {
     int32_t n_work = 0, n_split = 0;
     float* split_partial = nullptr;
     int32_t* split_rows = nullptr;
+    int32_t* split_list = nullptr;   // the block rows that are sliced (fix-up kernel runs over these only)
+    int32_t n_split_rows = 0;
     int32_t max_row_blocks = 0;
     void* host_pipe = nullptr;  // HostPipe (spmv.cu): streams, events and staging buffers of bmsp_spmv_host
 };

@@ -9,11 +9,14 @@
 
 namespace bmsp {
 
+// SpMV cost of a block row in byte units: its blocks and values, plus a per-row term.  The row-tiled kernel pays little per row
+// (row pointers, y); the block-parallel kernel spends a whole warp on every block row, worth about 20 blocks of streaming
+// (fitted on the R-MAT-22 shards of a 4-GPU run: 9.95 us per 10^6 blocks + 25 us per 10^6 matrix rows).
 __global__ void spmv_weight_kernel(const int32_t* __restrict__ brp, const uint32_t* __restrict__ rvb, int nbr, int vsize,
-                                   uint64_t* __restrict__ w) {
+                                   uint64_t row_cost, uint64_t* __restrict__ w) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nbr) return;
-    w[r] = (uint64_t)(brp[r + 1] - brp[r]) * 12 + (uint64_t)(rvb[r + 1] - rvb[r]) * vsize + 8 + 32;
+    w[r] = (uint64_t)(brp[r + 1] - brp[r]) * 12 + (uint64_t)(rvb[r + 1] - rvb[r]) * vsize + row_cost;
 }
 
 // candidate SpGEMM pairs per A block row (warp per row)
@@ -53,7 +56,10 @@ extern "C" int bmsp_partition_block_rows(bmsp_matrix_t A, bmsp_matrix_t Bt, int3
     uint64_t* w = nullptr;
     BMSP_TRY(dev_alloc_t(&w, (size_t)nbr + 2, st));
     if (weight_spgemm) cand_weight_kernel<<<(unsigned)ceil_div(nbr, 8), 256, 0, st>>>(A->brp, A->bcol, Bt->brp, nbr, w);
-    else spmv_weight_kernel<<<(unsigned)ceil_div(nbr, 256), 256, 0, st>>>(A->brp, A->rvb, nbr, A->dtype == BMSP_F16 ? 2 : 4, w);
+    else {
+        const bool blockpar = A->nblk > 0 && (double)A->nnz / (double)A->nblk < 2.5;      // same rule as plan_spmv
+        spmv_weight_kernel<<<(unsigned)ceil_div(nbr, 256), 256, 0, st>>>(A->brp, A->rvb, nbr, A->dtype == BMSP_F16 ? 2 : 4, blockpar ? 288 : 40, w);
+    }
     BMSP_KERNEL_CHECK();
     BMSP_TRY(exclusive_scan_u64(w, w, nbr, st));
     std::vector<uint64_t> h((size_t)nbr + 1);

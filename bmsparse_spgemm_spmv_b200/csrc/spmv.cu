@@ -689,15 +689,21 @@ __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __re
 }
 
 // sliced block rows: sum the slices' partials in slice order (deterministic), one thread per matrix row
+__global__ void split_list_kernel(const int32_t* __restrict__ item_ofs, int nbr, int32_t* __restrict__ list, int32_t* __restrict__ count) {
+    const int br = blockIdx.x * blockDim.x + threadIdx.x;
+    if (br < nbr && item_ofs[br + 1] - item_ofs[br] > 1) list[atomicAdd(count, 1)] = br;
+}
+
 template <typename H = NoHalo>
-__global__ void spmv_fixup_kernel(const int32_t* __restrict__ item_ofs, const float* __restrict__ partial, int nbr, int rows,
-                                  float* __restrict__ y, const H hd) {
+__global__ void spmv_fixup_kernel(const int32_t* __restrict__ item_ofs, const float* __restrict__ partial, const int32_t* __restrict__ split_list,
+                                  int n_split_rows, int rows, float* __restrict__ y, const H hd) {
     constexpr bool DIST = !std::is_same<H, NoHalo>::value;     // multi-GPU variant: the finished rows also go to the peers
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row < rows) {
-        const int br = (int)(row >> 3), r = (int)(row & 7);
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((gt >> 3) < n_split_rows) {
+        const int br = split_list[gt >> 3], r = gt & 7;
+        const int64_t row = (int64_t)br * 8 + r;
         const int i0 = item_ofs[br], i1 = item_ofs[br + 1];
-        if (i1 - i0 > 1) {
+        if (row < rows) {
             float s = 0.f;
             for (int i = i0; i < i1; i++) s += partial[(int64_t)i * 8 + r];
             y[row] = s;
@@ -794,7 +800,16 @@ int plan_spmv(bmsp_matrix_s* m, cudaStream_t st) {
     work_fill_kernel<<<(unsigned)ceil_div(m->nbr, 256), 256, 0, st>>>(m->brp, m->nbr, cnt, (int4*)m->work);
     BMSP_KERNEL_CHECK();
     m->split_rows = (int32_t*)cnt;           // item offsets per block row, kept for the fix-up
-    if (m->n_split > 0) BMSP_TRY(dev_alloc_t(&m->split_partial, (size_t)total * 8, st));
+    if (m->n_split > 0) {
+        BMSP_TRY(dev_alloc_t(&m->split_partial, (size_t)total * 8, st));
+        BMSP_TRY(dev_alloc_t(&m->split_list, (size_t)m->n_split + 1, st));      // a sliced row adds at least one item
+        int32_t* cntr = m->split_list + m->n_split;
+        BMSP_CUDA(cudaMemsetAsync(cntr, 0, sizeof(int32_t), st));
+        split_list_kernel<<<(unsigned)ceil_div(m->nbr, 256), 256, 0, st>>>(m->split_rows, m->nbr, m->split_list, cntr);
+        BMSP_KERNEL_CHECK();
+        BMSP_CUDA(cudaMemcpyAsync(&m->n_split_rows, cntr, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        BMSP_CUDA(cudaStreamSynchronize(st));
+    }
     return BMSP_OK;
 }
 
@@ -838,14 +853,14 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, 
         }
         return launch_tile_kernel<T, X, 64, 2, 12, H>(a, x, y, hd, grid, smem, st);
     }
-    const unsigned grid1 = (unsigned)ceil_div(A->n_work, 8), grid2 = (unsigned)ceil_div(A->rows, 256);
+    const unsigned grid1 = (unsigned)ceil_div(A->n_work, 8), grid2 = (unsigned)ceil_div((int64_t)A->n_split_rows * 8, 256);
     constexpr bool DIST = !std::is_same<H, NoHalo>::value;
     if constexpr (DIST) { halo_wait_kernel<<<1, 32, 0, st>>>(hd); BMSP_KERNEL_CHECK(); }
     spmv_blockpar_kernel<T, X, H><<<grid1, 256, 0, st>>>(A->bmps, A->bcol, A->offsets, (const T*)A->values, (const int4*)A->work, A->n_work,
                                                        A->rows, x, y, A->split_partial, hd);
     BMSP_KERNEL_CHECK();
     if (A->n_split > 0) {
-        spmv_fixup_kernel<H><<<grid2, 256, 0, st>>>(A->split_rows, A->split_partial, A->nbr, A->rows, y, hd);
+        spmv_fixup_kernel<H><<<grid2, 256, 0, st>>>(A->split_rows, A->split_partial, A->split_list, A->n_split_rows, A->rows, y, hd);
         BMSP_KERNEL_CHECK();
     }
     if constexpr (DIST) { halo_flag_kernel<<<1, 32, 0, st>>>(hd); BMSP_KERNEL_CHECK(); }
