@@ -41,6 +41,7 @@ struct GemmArgs {
     int32_t* work_counter;
     const int32_t* row_list;   // when set: the rows to process, in this order (heavy-row / light-row launches); else row_begin + i
     int32_t n_list;
+    int32_t batch;             // rows a CTA takes from the queue per atomic (tiny rows: the queue head would serialise the launch)
     uint32_t* row_count;       // COUNT out: C blocks per row (indexed row - row_begin)
     uint32_t* row_surv;        // COUNT out: surviving pairs per row; FILL/NUMERIC in: exclusive scan of it
     uint2* surv_list;          // FILL out / NUMERIC in: (A block, B block) of every surviving pair, row-segmented
@@ -462,14 +463,17 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
     uint32_t* s_tmp = reinterpret_cast<uint32_t*>(s_dense + (PASS == PASS_NUMERIC_MMA ? g.cap_c * 64 : 0)); // [34]
     int* s_row = reinterpret_cast<int*>(s_tmp + 34);
     uint32_t* s_cursor = reinterpret_cast<uint32_t*>(s_row + 1);
+    int* s_batch = s_row + 2;                          // [0] next queue index of this CTA's batch, [1] its end
+    if (tid == 0) { s_batch[0] = 0; s_batch[1] = 0; }
 
     unsigned long long n_cand = 0, n_surv_total = 0;
     uint2* q = s_queue + wid * QSLOTS;
 
     while (true) {
         if (tid == 0) {
-            const int i = atomicAdd(g.work_counter, 1);
-            *s_row = g.row_list ? (i < g.n_list ? g.row_list[i] : g.row_end) : g.row_begin + i;
+            if (s_batch[0] == s_batch[1]) { s_batch[0] = atomicAdd(g.work_counter, g.batch); s_batch[1] = s_batch[0] + g.batch; }
+            const int i = s_batch[0]++;
+            *s_row = g.row_list ? (i < g.n_list ? g.row_list[i] : g.row_end) : (i < g.row_end - g.row_begin ? g.row_begin + i : g.row_end);
             *s_cursor = 0;
         }
         __syncthreads();
@@ -674,7 +678,7 @@ template <int PASS>
 static int launch_pass(GemmArgs& g, int T, int sms, cudaStream_t st, const RowSplit& sp) {
     if (!sp.active) return launch_pass_t<PASS, 256>(g, T, sms, g.row_end - g.row_begin, st);
     GemmArgs gh = g, gl = g;
-    gh.row_list = sp.list; gh.n_list = sp.n_heavy; gh.work_counter = g.work_counter + 1; gh.G = 32;
+    gh.row_list = sp.list; gh.n_list = sp.n_heavy; gh.work_counter = g.work_counter + 1; gh.G = 32; gh.batch = 1;
     if (g.g_bitset) { gh.g_bitset = g.g_bitset + sp.heavy_scratch_off; gh.g_wrank = g.g_wrank + sp.heavy_scratch_off; }
     gl.row_list = sp.list + sp.n_heavy; gl.n_list = sp.n_light;
     BMSP_CUDA(cudaEventRecord(sp.fork, st));
@@ -800,6 +804,8 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     g.a_brp = A->brp; g.a_bcol = A->bcol; g.a_bmps = A->bmps; g.a_kmask = A->kmask; g.a_off = A->offsets; g.a_val = (const __half*)A->values;
     g.b_brp = Bt->brp; g.b_bcol = Bt->bcol; g.b_bmps = Bt->bmps; g.b_kmask = Bt->kmask; g.b_off = Bt->offsets; g.b_val = (const __half*)Bt->values;
     g.rowinfo = rowinfo; g.row_begin = rb; g.row_end = re; g.G = G;
+    // P4096 A*A: 2.1 M block rows of 25 candidate pairs -- one atomic on the queue head per row and pass cost more than the rows
+    g.batch = avg_cand <= 96 ? 32 : (avg_cand <= 2048 ? 4 : 1);
     g.cap_words = max_words <= 8192 ? std::max(1, max_words) : (avg_words > 4096.0 ? 256 : 8192);
     g.cap_c = 0; g.cap_nnz = 0;
     g.max_words = max_words;
