@@ -41,7 +41,11 @@ struct GemmArgs {
     int32_t* work_counter;
     const int32_t* row_list;   // when set: the rows to process, in this order (heavy-row / light-row launches); else row_begin + i
     int32_t n_list;
-    int32_t batch;             // rows a CTA takes from the queue per atomic (tiny rows: the queue head would serialise the launch)
+    int32_t batch;             // work items a CTA takes from the queue per atomic (tiny rows: the queue head would serialise the launch)
+    int32_t split8;            // NUMERIC: 8 lanes per surviving pair, one per row of the A block (blocks with >= 4 values: a lane
+                               // that multiplies a whole pair alone walks up to 64 x 8 dependent loads)
+    int32_t group;             // consecutive block rows per work item (1..32): tiny rows are processed a group at a time -- one bit set, one
+                               // pair-list segment, one set of accumulators for the group -- so that a CTA has hundreds of pairs in flight
     uint32_t* row_count;       // COUNT out: C blocks per row (indexed row - row_begin)
     uint32_t* row_surv;        // COUNT out: surviving pairs per row; FILL/NUMERIC in: exclusive scan of it
     uint2* surv_list;          // FILL out / NUMERIC in: (A block, B block) of every surviving pair, row-segmented
@@ -105,38 +109,52 @@ __global__ void pack_meta_kernel(const uint64_t* __restrict__ bmps, const int32_
     pm[i] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)bcol[i], (uint32_t)off[i]);
 }
 
-// P0: warp per A block row: candidate pairs, and the span [jmin, jmax] of C block columns.
+// P0: warp per A block row (grid-stride): candidate pairs, and the span [jmin, jmax] of C block columns.  The statistics are
+// reduced per warp and per CTA before they touch global memory: with one global atomic -- or even one volatile load -- per row,
+// the 2.1 M rows of P4096 serialise on three L2 addresses (3.7 ms for a kernel that otherwise takes 0.3 ms).
 __global__ void __launch_bounds__(256) rowinfo_kernel(const int32_t* __restrict__ a_brp, const int32_t* __restrict__ a_bcol,
                                                       const int32_t* __restrict__ b_brp, const int32_t* __restrict__ b_bcol,
                                                       int row_begin, int row_end, int2* __restrict__ rowinfo,
                                                       unsigned long long* __restrict__ cand, int* __restrict__ maxes,
                                                       unsigned long long* __restrict__ sum_words, unsigned long long* __restrict__ max_cand) {
+    __shared__ unsigned long long s_words, s_maxc;
+    __shared__ int s_maxw;
     const int lane = threadIdx.x & 31;
-    const int row = row_begin + blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= row_end) return;
-    int jmin = 0x7FFFFFFF, jmax = -1;
-    unsigned long long c = 0;
-    for (int a = a_brp[row] + lane; a < a_brp[row + 1]; a += 32) {
-        const int k = a_bcol[a];
-        const int b0 = b_brp[k], b1 = b_brp[k + 1];
-        if (b1 > b0) {
-            c += (unsigned long long)(b1 - b0);
-            jmin = min(jmin, b_bcol[b0]);
-            jmax = max(jmax, b_bcol[b1 - 1]);
+    if (threadIdx.x == 0) { s_words = 0; s_maxc = 0; s_maxw = 0; }
+    __syncthreads();
+    unsigned long long w_sum = 0, w_maxc = 0;
+    int w_maxw = 0;
+    for (int row = row_begin + blockIdx.x * 8 + (threadIdx.x >> 5); row < row_end; row += gridDim.x * 8) {
+        int jmin = 0x7FFFFFFF, jmax = -1;
+        unsigned long long c = 0;
+        for (int a = a_brp[row] + lane; a < a_brp[row + 1]; a += 32) {
+            const int k = a_bcol[a];
+            const int b0 = b_brp[k], b1 = b_brp[k + 1];
+            if (b1 > b0) {
+                c += (unsigned long long)(b1 - b0);
+                jmin = min(jmin, b_bcol[b0]);
+                jmax = max(jmax, b_bcol[b1 - 1]);
+            }
+        }
+        for (int o = 16; o; o >>= 1) {
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+            jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, o));
+            jmax = max(jmax, __shfl_xor_sync(0xffffffffu, jmax, o));
+        }
+        if (lane == 0) {
+            int jbase = 0, words = 0;
+            if (jmax >= 0) { jbase = jmin & ~31; words = ((jmax - jbase) >> 5) + 1; }
+            rowinfo[row - row_begin] = make_int2(jbase, words);
+            cand[row - row_begin] = c;
+            w_maxw = max(w_maxw, words); w_sum += (unsigned long long)words; w_maxc = max(w_maxc, c);
         }
     }
-    for (int o = 16; o; o >>= 1) {
-        c += __shfl_xor_sync(0xffffffffu, c, o);
-        jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, o));
-        jmax = max(jmax, __shfl_xor_sync(0xffffffffu, jmax, o));
-    }
-    if (lane == 0) {
-        int jbase = 0, words = 0;
-        if (jmax >= 0) { jbase = jmin & ~31; words = ((jmax - jbase) >> 5) + 1; }
-        rowinfo[row - row_begin] = make_int2(jbase, words);
-        cand[row - row_begin] = c;
-        atomicMax(maxes, words);
-        if (words) { atomicAdd(sum_words, (unsigned long long)words); atomicMax(max_cand, c); }
+    if (lane == 0) { atomicMax(&s_maxw, w_maxw); atomicAdd(&s_words, w_sum); atomicMax(&s_maxc, w_maxc); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_maxw) atomicMax(maxes, s_maxw);
+        if (s_words) atomicAdd(sum_words, s_words);
+        if (s_maxc) atomicMax(max_cand, s_maxc);
     }
 }
 
@@ -175,7 +193,12 @@ __device__ __forceinline__ uint32_t rank_words(const uint32_t* bitset, uint32_t*
 
 // Per-row state shared by the enumeration modes.
 struct RowCtx {
-    int row, a0, a1, jbase, c0;
+    int row, nr;         // first block row of the work item and the number of rows in it
+    int a0, a1, jbase, c0;
+    const int* abr;      // [nr+1] a_brp of the rows                        (shared)
+    const int* jb;       // [nr]   first C block column of each row's bit set
+    const int* wo;       // [nr+1] word offset of each row's bit set inside the work item's
+    uint32_t* rsurv;     // [nr]   COUNT: surviving pairs per row
     uint32_t* bitset; uint32_t* wrank;
     uint64_t* cbmp;      // FILL: staging (shared or global C.bmps+c0); NUMERIC: shared copy or null
     uint32_t* coff;      // NUMERIC: value offsets relative to the row, or null (global mode)
@@ -183,13 +206,22 @@ struct RowCtx {
     float* dense;        // NUMERIC_MMA: [ccount][64] fp32, lane-private slots (cell (r,c) at (c*4 + r/2) + 32*(r&1))
 };
 
+// index of the row of a work item that owns v, given the rows' ascending start offsets (A blocks, bit-set words or C blocks)
+__device__ __forceinline__ int local_row(const int* bounds, int nr, int v) {
+    int rl = 0;
+    while (rl + 1 < nr && v >= bounds[rl + 1]) rl++;
+    return rl;
+}
+
 template <int MODE>
-__device__ __forceinline__ void process_pair(const GemmArgs& g, const RowCtx& r, int a, int b) {
+__device__ __forceinline__ void process_pair(const GemmArgs& g, const RowCtx& r, int a, int b, int arow = -1) {
     const uint4 pm = __ldg(g.b_pm + b);
     const uint64_t abmp = g.a_bmps[a], bbmp = ((uint64_t)pm.y << 32) | pm.x;
-    const int j = (int)pm.z - r.jbase;
-    const uint32_t word = r.bitset[j >> 5];
-    const int c = (int)r.wrank[j >> 5] + __popc(word & ((1u << (j & 31)) - 1u));
+    const int rl = local_row(r.abr, r.nr, a);
+    const int j = (int)pm.z - r.jb[rl];
+    const int wi = r.wo[rl] + (j >> 5);
+    const uint32_t word = r.bitset[wi];
+    const int c = (int)r.wrank[wi] + __popc(word & ((1u << (j & 31)) - 1u));
     if (MODE == MODE_FILL) {
         const uint64_t pb = pair_bitmap(abmp, bbmp);
         unsigned int* w = reinterpret_cast<unsigned int*>(&r.cbmp[c]);      // native 32-bit ATOMS.OR, not a 64-bit CAS loop
@@ -203,6 +235,11 @@ __device__ __forceinline__ void process_pair(const GemmArgs& g, const RowCtx& r,
         else { cb = g.c_bmps[r.c0 + c]; dst = g.c_val + g.c_off[r.c0 + c]; }
         uint64_t rem = abmp;
         int ka = 0;
+        if (arow >= 0) {                                    // this lane's row of the A block only
+            rem = abmp & (0xFF00000000000000ull >> (8 * arow));
+            ka = arow ? __popcll(abmp >> (64 - 8 * arow)) : 0;
+            if (!rem) return;
+        }
         while (rem) {
             const int p = __clzll((long long)rem);
             rem &= ~(0x8000000000000000ull >> p);
@@ -305,11 +342,12 @@ __device__ __forceinline__ void enumerate_vec(const GemmArgs& g, const RowCtx& r
     const int niter = (r.a1 - r.a0 + slots - 1) / slots;
     for (int itA = 0; itA < niter; itA++) {
         const int a = r.a0 + itA * slots + slot;
-        int b0 = 0, b1 = 0; uint32_t am4 = 0;
+        int b0 = 0, b1 = 0, rl = 0, jb = 0, wb = 0; uint32_t am4 = 0;
         if (a < r.a1) {
             const int k = g.a_bcol[a];
             b0 = g.b_brp[k]; b1 = g.b_brp[k + 1];
             am4 = (uint32_t)g.a_kmask[a] * 0x01010101u;
+            rl = local_row(r.abr, r.nr, a); jb = r.jb[rl]; wb = r.wo[rl];
         }
         const int bs = b0 & ~3;
         int ngrp = (b1 - bs + 3) >> 2;           // 4-block groups of this lane's B row (0 when the row is empty)
@@ -329,7 +367,7 @@ __device__ __forceinline__ void enumerate_vec(const GemmArgs& g, const RowCtx& r
                 if (STATS) { n_cand += (unsigned)(hi - lo); }
             }
             const int cnt = __popc(nz) >> 3;
-            if (STATS) n_surv += cnt;
+            if (STATS) { n_surv += cnt; if (r.nr > 1 && cnt) atomicAdd(&r.rsurv[rl], (uint32_t)cnt); }   // single row: reduced by the caller
             uint32_t rem = nz;
             if (LIST) {
                 // recompute per-byte positions without packing tricks (at most 4 survivors per lane)
@@ -353,8 +391,8 @@ __device__ __forceinline__ void enumerate_vec(const GemmArgs& g, const RowCtx& r
             while (rem) {
                 const int i = (__ffs(rem) - 1) >> 3;
                 rem &= ~(0xFFu << (8 * i));
-                const int j = g.b_bcol[bb + i] - r.jbase;
-                atomicOr(&r.bitset[j >> 5], 1u << (j & 31));
+                const int j = g.b_bcol[bb + i] - jb;
+                atomicOr(&r.bitset[wb + (j >> 5)], 1u << (j & 31));
             }
         }
     }
@@ -456,24 +494,35 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
     uint64_t* s_cbmp = reinterpret_cast<uint64_t*>(smem);                                        // [cap_c]     FILL, NUMERIC
     uint2* s_queue = reinterpret_cast<uint2*>(s_cbmp + (HAS_CBMP ? g.cap_c : 0));                 // [nwarps*QSLOTS] NUMERIC_MMA
     uint32_t* s_bitset = reinterpret_cast<uint32_t*>(s_queue + (HAS_QUEUE ? nwarps * QSLOTS : 0)); // [cap_words]
-    uint32_t* s_wrank = s_bitset + g.cap_words;                                                   // [cap_words] all but COUNT
-    uint32_t* s_coff = s_wrank + (PASS == PASS_COUNT ? 0 : g.cap_words);                          // [cap_c]     NUMERIC
+    uint32_t* s_wrank = s_bitset + g.cap_words;                                                   // [cap_words] (COUNT: only for row groups)
+    uint32_t* s_coff = s_wrank + ((PASS == PASS_COUNT && g.group == 1) ? 0 : g.cap_words);        // [cap_c]     NUMERIC
     float* s_acc = reinterpret_cast<float*>(s_coff + (PASS == PASS_NUMERIC ? g.cap_c : 0));       // [cap_nnz]   NUMERIC
     float* s_dense = s_acc + (PASS == PASS_NUMERIC ? g.cap_nnz : 0);                              // [cap_c*64]  NUMERIC_MMA
     uint32_t* s_tmp = reinterpret_cast<uint32_t*>(s_dense + (PASS == PASS_NUMERIC_MMA ? g.cap_c * 64 : 0)); // [34]
     int* s_row = reinterpret_cast<int*>(s_tmp + 34);
     uint32_t* s_cursor = reinterpret_cast<uint32_t*>(s_row + 1);
     int* s_batch = s_row + 2;                          // [0] next queue index of this CTA's batch, [1] its end
+    // per-row tables of the work item (<= 32 rows): A block offsets, bit-set origin and word offsets, C block offsets, surviving
+    // pairs, value offsets
+    int* s_abr = s_row + 4;                            // [33]
+    int* s_jb = s_abr + 33;                            // [32]
+    int* s_wo = s_jb + 32;                             // [33]
+    int* s_cbr = s_wo + 33;                            // [33]
+    uint32_t* s_rsurv = reinterpret_cast<uint32_t*>(s_cbr + 33);   // [32]
+    uint32_t* s_rowoff = s_rsurv + 32;                 // [33]
     if (tid == 0) { s_batch[0] = 0; s_batch[1] = 0; }
 
     unsigned long long n_cand = 0, n_surv_total = 0;
+    int my_max1 = 0, my_max2 = 0, my_max3 = 0;         // per-thread maxima, published once when the CTA retires
     uint2* q = s_queue + wid * QSLOTS;
+    const int R = g.row_list ? 1 : g.group;
+    const int n_items = g.row_list ? g.n_list : (g.row_end - g.row_begin + R - 1) / R;
 
     while (true) {
         if (tid == 0) {
             if (s_batch[0] == s_batch[1]) { s_batch[0] = atomicAdd(g.work_counter, g.batch); s_batch[1] = s_batch[0] + g.batch; }
             const int i = s_batch[0]++;
-            *s_row = g.row_list ? (i < g.n_list ? g.row_list[i] : g.row_end) : (i < g.row_end - g.row_begin ? g.row_begin + i : g.row_end);
+            *s_row = i < n_items ? (g.row_list ? g.row_list[i] : g.row_begin + i * R) : g.row_end;
             *s_cursor = 0;
         }
         __syncthreads();
@@ -481,14 +530,31 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
         r.row = *s_row;
         __syncthreads();
         if (r.row >= g.row_end) break;
+        r.nr = min(R, g.row_end - r.row);
+        const int nr = r.nr;
         const int lrow = r.row - g.row_begin;
-        const int2 ri = g.rowinfo[lrow];
-        r.jbase = ri.x;
-        const int nwords = ri.y;
-        r.a0 = g.a_brp[r.row]; r.a1 = g.a_brp[r.row + 1];
+        // ---- the rows of this work item
+        if (tid < 32) {
+            int nw = 0;
+            if (tid < nr) { const int2 ri = g.rowinfo[lrow + tid]; s_jb[tid] = ri.x; nw = ri.y; s_rsurv[tid] = 0; }
+            int inc = nw;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (tid < nr) s_wo[tid + 1] = inc;
+            if (tid == 0) s_wo[0] = 0;
+            if (tid <= nr) {
+                s_abr[tid] = g.a_brp[r.row + tid];
+                if (PASS != PASS_COUNT) s_cbr[tid] = g.c_brp[lrow + tid];
+                if (PASS == PASS_NUMERIC || PASS == PASS_NUMERIC_MMA) s_rowoff[tid] = (uint32_t)(g.row_nnz[lrow + tid] - g.row_nnz[lrow]);
+            }
+        }
+        __syncthreads();
+        const int nwords = s_wo[nr];
+        r.a0 = s_abr[0]; r.a1 = s_abr[nr]; r.jbase = s_jb[0];
+        r.abr = s_abr; r.jb = s_jb; r.wo = s_wo; r.rsurv = s_rsurv;
         if (nwords == 0) {
-            if (PASS == PASS_COUNT && tid == 0) { g.row_count[lrow] = 0; g.row_surv[lrow] = 0; }
-            if (PASS == PASS_FILL && tid == 0) g.row_nnz[lrow] = 0;
+            if (PASS == PASS_COUNT && tid < nr) { g.row_count[lrow + tid] = 0; g.row_surv[lrow + tid] = 0; }
+            if (PASS == PASS_FILL && tid < nr) g.row_nnz[lrow + tid] = 0;
             continue;
         }
         const bool wfit = nwords <= g.cap_words;
@@ -499,31 +565,43 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
         int ccount = 0;
         uint32_t s0 = 0, nsurv = 0;
         if (PASS != PASS_COUNT) {
-            r.c0 = g.c_brp[lrow]; ccount = g.c_brp[lrow + 1] - r.c0;
-            s0 = g.row_surv[lrow]; nsurv = g.row_surv[lrow + 1] - s0;
+            r.c0 = s_cbr[0]; ccount = s_cbr[nr] - r.c0;
+            s0 = g.row_surv[lrow]; nsurv = g.row_surv[lrow + nr] - s0;
         }
         if (PASS != PASS_COUNT && ccount == 0) {
-            if (PASS == PASS_FILL && tid == 0) g.row_nnz[lrow] = 0;
+            if (PASS == PASS_FILL && tid < nr) g.row_nnz[lrow + tid] = 0;
             __syncthreads();
             continue;
         }
         uint2* list = g.surv_list + s0;
+        const int c0 = r.c0;                           // s_cbr holds absolute C block offsets; c - c0 is the index inside the work item
 
         if (PASS == PASS_COUNT) {
             __syncthreads();
             uint32_t ns = 0;
-            enumerate_vec<false, true>(g, r, nullptr, nullptr, n_cand, ns);
+            enumerate_vec<false, true>(g, r, nullptr, nullptr, n_cand, ns);      // bits; survivors per row into s_rsurv
             n_surv_total += ns;
+            if (nr == 1) {
 #pragma unroll
-            for (int o = 16; o; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
-            if (lane == 0 && ns) atomicAdd(s_cursor, ns);
+                for (int o = 16; o; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+                if (lane == 0 && ns) atomicAdd(&s_rsurv[0], ns);
+            }
             __syncthreads();
-            const uint32_t total = rank_words(r.bitset, nullptr, nwords, s_tmp);
-            if (tid == 0) { g.row_count[lrow] = total; g.row_surv[lrow] = *s_cursor; atomicMax(g.maxes + 1, (int)total); }
+            const uint32_t total = rank_words(r.bitset, nr > 1 ? r.wrank : nullptr, nwords, s_tmp);
+            if (tid < nr) {
+                uint32_t cnt = total;
+                if (nr > 1) {
+                    const int w0 = s_wo[tid], w1 = s_wo[tid + 1];
+                    cnt = (w1 < nwords ? r.wrank[w1] : total) - (w0 < nwords ? r.wrank[w0] : total);
+                }
+                g.row_count[lrow + tid] = cnt; g.row_surv[lrow + tid] = s_rsurv[tid];
+                my_max3 = max(my_max3, (int)cnt);                                // largest single row (dense-block NUMERIC runs row by row)
+            }
+            if (tid == 0) my_max1 = max(my_max1, (int)total);
         }
         if (PASS == PASS_FILL) {
             const bool cfit = ccount <= g.cap_c;
-            r.cbmp = cfit ? s_cbmp : g.c_bmps + r.c0;          // global C.bmps is pre-zeroed
+            r.cbmp = cfit ? s_cbmp : g.c_bmps + c0;            // global C.bmps is pre-zeroed
             if (cfit) for (int c = tid; c < ccount; c += T) r.cbmp[c] = 0;
             __syncthreads();
             uint32_t ns = 0;
@@ -532,37 +610,47 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
             rank_words(r.bitset, r.wrank, nwords, s_tmp);
             for (uint32_t e = tid; e < nsurv; e += T) { const uint2 pr = list[e]; process_pair<MODE_FILL>(g, r, (int)pr.x, (int)pr.y); }
             __syncthreads();
-            // keys, bitmaps and the derived per-block arrays out: ascending bit index = ascending block column
+            // keys, bitmaps and the derived per-block arrays out: ascending (row, bit index) = ascending key
             for (int w = tid; w < nwords; w += T) {
                 uint32_t word = r.bitset[w];
+                if (!word) continue;
                 int c = (int)r.wrank[w];
+                const int rl = local_row(s_wo, nr, w);
+                const int jw = s_jb[rl] + (w - s_wo[rl]) * 32;
                 while (word) {
                     const int bit = __ffs(word) - 1;
                     word &= word - 1;
-                    const int j = r.jbase + w * 32 + bit;
+                    const int j = jw + bit;
                     const uint64_t bm = r.cbmp[c];
-                    g.c_keys[r.c0 + c] = ((uint64_t)(uint32_t)r.row << 32) | (uint32_t)j;
-                    g.c_bcol[r.c0 + c] = j;
-                    g.c_kmask[r.c0 + c] = (uint8_t)kmask_of(bm);
-                    if (cfit) g.c_bmps[r.c0 + c] = bm;
+                    g.c_keys[c0 + c] = ((uint64_t)(uint32_t)(r.row + rl) << 32) | (uint32_t)j;
+                    g.c_bcol[c0 + c] = j;
+                    g.c_kmask[c0 + c] = (uint8_t)kmask_of(bm);
+                    if (cfit) g.c_bmps[c0 + c] = bm;
                     c++;
                 }
             }
             __syncthreads();
-            // value offsets relative to the row (NUMERIC rebases them once the row totals are scanned)
-            const uint32_t rn = scan_popc64(r.cbmp, g.c_off + r.c0, ccount, s_tmp);
-            if (tid == 0) { g.row_nnz[lrow] = rn; atomicMax(g.maxes + 2, (int)min(rn, 0x7FFFFFFFu)); }
+            // value offsets: scanned over the work item, then made relative to each block's own row (NUMERIC rebases them once the
+            // row totals are scanned)
+            const uint32_t rn = scan_popc64(r.cbmp, g.c_off + c0, ccount, s_tmp);
+            if (tid <= nr) { const int cs = s_cbr[tid] - c0; s_rowoff[tid] = cs < ccount ? (uint32_t)g.c_off[c0 + cs] : rn; }
+            __syncthreads();
+            if (nr > 1)
+                for (int c = tid; c < ccount; c += T) g.c_off[c0 + c] -= s_rowoff[local_row(s_cbr, nr, c0 + c)];
+            if (tid < nr) g.row_nnz[lrow + tid] = s_rowoff[tid + 1] - s_rowoff[tid];
+            if (tid == 0) my_max2 = max(my_max2, (int)min(rn, 0x7FFFFFFFu));
         }
         if (PASS == PASS_NUMERIC || PASS == PASS_NUMERIC_MMA) {
             const uint64_t vbase = g.row_nnz[lrow];
-            const int64_t rownnz = (int64_t)(g.row_nnz[lrow + 1] - vbase);
+            const int64_t rownnz = (int64_t)(g.row_nnz[lrow + nr] - vbase);
             const bool fit = PASS == PASS_NUMERIC ? (ccount <= g.cap_c && rownnz <= g.cap_nnz) : (ccount <= g.cap_c);
             for (int c = tid; c < ccount; c += T) {
-                const uint64_t local = g.c_off[r.c0 + c];
-                if (PASS == PASS_NUMERIC && fit) { s_cbmp[c] = g.c_bmps[r.c0 + c]; s_coff[c] = (uint32_t)local; }
-                g.c_off[r.c0 + c] = vbase + local;                           // absolute from here on
-                const int j = g.c_bcol[r.c0 + c] - r.jbase;                 // bit set from C's own block columns
-                atomicOr(&r.bitset[j >> 5], 1u << (j & 31));
+                const int rl = local_row(s_cbr, nr, c0 + c);
+                const uint64_t local = s_rowoff[rl] + g.c_off[c0 + c];      // relative to the work item's first value
+                if (PASS == PASS_NUMERIC && fit) { s_cbmp[c] = g.c_bmps[c0 + c]; s_coff[c] = (uint32_t)local; }
+                g.c_off[c0 + c] = vbase + local;                             // absolute from here on
+                const int j = g.c_bcol[c0 + c] - s_jb[rl];                   // bit set from C's own block columns
+                atomicOr(&r.bitset[s_wo[rl] + (j >> 5)], 1u << (j & 31));
             }
             if (PASS == PASS_NUMERIC && fit) {
                 r.cbmp = s_cbmp; r.coff = s_coff; r.acc = s_acc;
@@ -574,8 +662,17 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
             }
             __syncthreads();
             rank_words(r.bitset, r.wrank, nwords, s_tmp);
-            if (PASS == PASS_NUMERIC || !fit) {
-                for (uint32_t e = tid; e < nsurv; e += T) { const uint2 pr = list[e]; process_pair<MODE_NUMERIC>(g, r, (int)pr.x, (int)pr.y); }
+            if (PASS == PASS_NUMERIC) {
+                if (g.split8) {
+                    for (uint64_t e = tid; e < (uint64_t)nsurv * 8u; e += T) { const uint2 pr = list[e >> 3]; process_pair<MODE_NUMERIC>(g, r, (int)pr.x, (int)pr.y, (int)(e & 7u)); }
+                } else {
+                    for (uint32_t e = tid; e < nsurv; e += T) { const uint2 pr = list[e]; process_pair<MODE_NUMERIC>(g, r, (int)pr.x, (int)pr.y); }
+                }
+            } else if (!fit) {
+                // too many C blocks for the dense accumulators: scalar products into global memory.  The row's pairs are enumerated
+                // again rather than read from the pair list: FILL may have written the list a group of rows at a time
+                unsigned long long dc = 0, ds = 0;
+                enumerate_row<MODE_NUMERIC, false>(g, r, q, dc, ds);
             } else {
                 unsigned long long dc = 0, ds = 0;
                 enumerate_row<MODE_MMA, false>(g, r, q, dc, ds);          // one warp per block row: pairs of an A block stay adjacent
@@ -586,8 +683,8 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
                 // compact the dense accumulators through C's bitmaps: slot L <-> cell (r = 2t, c = g), slot L+32 <-> (2t+1, g)
                 const int P0 = (lane & 3) * 16 + (lane >> 2);
                 for (int c = wid; c < ccount; c += nwarps) {
-                    const uint64_t bmp = g.c_bmps[r.c0 + c];
-                    float* dst = g.c_val + g.c_off[r.c0 + c];
+                    const uint64_t bmp = g.c_bmps[c0 + c];
+                    float* dst = g.c_val + g.c_off[c0 + c];
                     if ((bmp >> (63 - P0)) & 1ull) dst[rank64(bmp, P0)] = s_dense[c * 64 + lane];
                     if ((bmp >> (55 - P0)) & 1ull) dst[rank64(bmp, P0 + 8)] = s_dense[c * 64 + 32 + lane];
                 }
@@ -595,6 +692,9 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
         }
         __syncthreads();
     }
+    if (my_max1) atomicMax(g.maxes + 1, my_max1);
+    if (my_max2) atomicMax(g.maxes + 2, my_max2);
+    if (my_max3) atomicMax(g.maxes + 3, my_max3);
     if (PASS == PASS_COUNT) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) { n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o); n_surv_total += __shfl_xor_sync(0xffffffffu, n_surv_total, o); }
@@ -602,15 +702,14 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
     }
 }
 
-static size_t pass_smem_bytes(int pass, int T, int cap_words, int cap_c, int cap_nnz) {
+static size_t pass_smem_bytes(int pass, int T, int cap_words, int cap_c, int cap_nnz, int group) {
     size_t s = 0;
     if (pass == PASS_FILL || pass == PASS_NUMERIC) s += (size_t)cap_c * 8;
     if (pass == PASS_NUMERIC_MMA) s += (size_t)(T / 32) * QSLOTS * 8;
-    s += (size_t)cap_words * 4;
-    if (pass != PASS_COUNT) s += (size_t)cap_words * 4;
+    s += (size_t)cap_words * ((pass == PASS_COUNT && group == 1) ? 4 : 8);
     if (pass == PASS_NUMERIC) s += (size_t)cap_c * 4 + (size_t)cap_nnz * 4;
     if (pass == PASS_NUMERIC_MMA) s += (size_t)cap_c * 64 * 4;
-    s += 36 * 4 + 16;
+    s += (38 + 33 + 32 + 33 + 33 + 32 + 33) * 4 + 16;      // s_tmp, row / cursor / batch words, the per-row tables
     return s;
 }
 
@@ -647,7 +746,7 @@ extern "C" int bmsp_debug_pair_bitmap(int64_t n, const uint64_t* a_host, const u
 
 template <int PASS, int MAXT>
 static int launch_pass_t(const GemmArgs& g, int T, int sms, int nrows, cudaStream_t st) {
-    const size_t smem = pass_smem_bytes(PASS, T, g.cap_words, g.cap_c, g.cap_nnz);
+    const size_t smem = pass_smem_bytes(PASS, T, g.cap_words, g.cap_c, g.cap_nnz, g.row_list ? 1 : g.group);
     auto kern = spgemm_pass_kernel<PASS, MAXT>;
     BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
     int occ = 0;
@@ -676,8 +775,9 @@ struct RowSplit {
 
 template <int PASS>
 static int launch_pass(GemmArgs& g, int T, int sms, cudaStream_t st, const RowSplit& sp) {
-    if (!sp.active) return launch_pass_t<PASS, 256>(g, T, sms, g.row_end - g.row_begin, st);
+    if (!sp.active) return launch_pass_t<PASS, 256>(g, T, sms, (int)ceil_div(g.row_end - g.row_begin, g.group), st);
     GemmArgs gh = g, gl = g;
+    gh.group = gl.group = 1;
     gh.row_list = sp.list; gh.n_list = sp.n_heavy; gh.work_counter = g.work_counter + 1; gh.G = 32; gh.batch = 1;
     if (g.g_bitset) { gh.g_bitset = g.g_bitset + sp.heavy_scratch_off; gh.g_wrank = g.g_wrank + sp.heavy_scratch_off; }
     gl.row_list = sp.list + sp.n_heavy; gl.n_list = sp.n_light;
@@ -746,7 +846,7 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
 
     int32_t h_small[16] = {0};
     if (nrows > 0) {
-        rowinfo_kernel<<<(unsigned)ceil_div(nrows, 8), 256, 0, st>>>(A->brp, A->bcol, Bt->brp, Bt->bcol, rb, re, rowinfo, cand, maxes, sum_words, max_cand);
+        rowinfo_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nrows, 8), (int64_t)sms * 8), 256, 0, st>>>(A->brp, A->bcol, Bt->brp, Bt->bcol, rb, re, rowinfo, cand, maxes, sum_words, max_cand);
         SG_CUDA(cudaGetLastError());
     }
     SG_CUDA(cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
@@ -790,7 +890,12 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     int G = 1;
     while (G < 32 && G * 4 < avgB) G <<= 1;
     const double avg_cand = avgA * avgB;
-    const int T = avg_cand <= 96 ? 32 : (avg_cand <= 2048 ? 128 : 256);
+    // Tiny rows (stencils: 25 candidate pairs per block row) are processed 16 rows at a time by 128-thread CTAs: one warp per row
+    // leaves the SM at 32 one-warp CTAs, each waiting on its own chain of dependent loads (P4096 A*A: 21.7 ms, cuSPARSE 13.0 ms)
+    int group = 1;
+    if (avg_cand <= 96 && !sp.active && (int64_t)16 * max_words <= 8192) group = 16;
+    if (const char* e = getenv("BMSP_SPGEMM_GROUP")) { const int v = atoi(e); if (v >= 1 && v <= 32 && !sp.active && (int64_t)v * max_words <= 8192) group = v; }
+    const int T = group > 1 ? 128 : (avg_cand <= 96 ? 32 : (avg_cand <= 2048 ? 128 : 256));
     if (G > T) G = T;
 
     if (!Bt->pmeta && Bt->nblk > 0) {      // built once per B operand, reused by later products
@@ -805,16 +910,18 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     g.b_brp = Bt->brp; g.b_bcol = Bt->bcol; g.b_bmps = Bt->bmps; g.b_kmask = Bt->kmask; g.b_off = Bt->offsets; g.b_val = (const __half*)Bt->values;
     g.rowinfo = rowinfo; g.row_begin = rb; g.row_end = re; g.G = G;
     // P4096 A*A: 2.1 M block rows of 25 candidate pairs -- one atomic on the queue head per row and pass cost more than the rows
-    g.batch = avg_cand <= 96 ? 32 : (avg_cand <= 2048 ? 4 : 1);
-    g.cap_words = max_words <= 8192 ? std::max(1, max_words) : (avg_words > 4096.0 ? 256 : 8192);
+    g.group = group;
+    g.split8 = A->nblk > 0 && (double)A->nnz / (double)A->nblk >= 4.0;
+    g.batch = group > 1 ? 2 : (avg_cand <= 96 ? 32 : (avg_cand <= 2048 ? 4 : 1));
+    g.cap_words = (int64_t)group * max_words <= 8192 ? std::max(1, group * max_words) : (avg_words > 4096.0 ? 256 : 8192);
     g.cap_c = 0; g.cap_nnz = 0;
-    g.max_words = max_words;
+    g.max_words = group * max_words;
     g.work_counter = counter; g.row_count = row_count; g.row_surv = row_surv; g.row_nnz = row_nnz; g.maxes = maxes; g.stats = stats;
 
-    if (max_words > g.cap_words) {
+    if (g.max_words > g.cap_words) {
         // over-cap rows use per-CTA global scratch; size it for the largest persistent grid (32 CTAs/SM)
-        sp.heavy_scratch_off = (size_t)sms * 32 * max_words;                  // + 2 heavy CTAs per SM
-        const size_t n = sp.heavy_scratch_off + (size_t)sms * 2 * max_words;
+        sp.heavy_scratch_off = (size_t)sms * 32 * g.max_words;                // + 2 heavy CTAs per SM
+        const size_t n = sp.heavy_scratch_off + (size_t)sms * 2 * g.max_words;
         SG_TRY(dev_alloc_t(&g_bitset, n, st));
         SG_TRY(dev_alloc_t(&g_wrank, n, st));
         g.g_bitset = g_bitset; g.g_wrank = g_wrank;
@@ -882,9 +989,12 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     if (path < 0) path = (dA * dB / 8.0 >= 40.0) ? 1 : 0;
     if (c_nnz > 0) {
         if (path == 1) {
-            g.cap_c = std::max(1, std::min(max_c, 192));
-            if (max_c > g.cap_c) SG_CUDA(cudaMemsetAsync(C->values, 0, (size_t)c_nnz * 4, st));
-            SG_TRY((launch_pass_t<PASS_NUMERIC_MMA, 256>(g, 32, sms, nrows, st)));
+            const int max_c_row = std::max(1, h_small[3]);                         // recorded by COUNT
+            g.cap_c = std::min(max_c_row, 192);
+            if (max_c_row > g.cap_c) SG_CUDA(cudaMemsetAsync(C->values, 0, (size_t)c_nnz * 4, st));
+            GemmArgs gm = g;
+            gm.group = 1; gm.batch = avg_cand <= 96 ? 32 : 1;          // one warp per block row: pairs of an A block stay adjacent
+            SG_TRY((launch_pass_t<PASS_NUMERIC_MMA, 256>(gm, 32, sms, nrows, st)));
         } else {
             const double avg_nnz = nrows ? (double)c_nnz / nrows : 0.0;
             if (max_c <= 4096 && max_rownnz <= 12288) { g.cap_c = std::max(1, max_c); g.cap_nnz = std::max(1, max_rownnz); }
