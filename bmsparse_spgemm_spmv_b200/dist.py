@@ -148,6 +148,26 @@ class ShardedSpMV:
         return self.own_slice(self.x[self.cur])
 
 
+def halo_descriptor(buf, rank, send, peers, own_lo, own_hi, ext_lo, my_base, peer_base, peer_layout, scratch_ptr, inbox=1024):
+    """bmsp_halo_desc of x buffer `buf` for one rank (pure address arithmetic: the CPU tests check it without a GPU).
+    send: [(peer, a, e)] global row ranges of mine a peer needs; peers: everybody I exchange epochs with (both directions);
+    peer_base[p]: where p's region is mapped here; peer_layout[p] = (buffer stride in bytes, p's ext_lo)."""
+    from . import _lib as L
+    d = L.HaloDesc()
+    d.n_push = len(send)
+    for i, (p, a, e) in enumerate(send):
+        stride, p_ext_lo = peer_layout[p]
+        d.push_lo[i] = a - own_lo; d.push_hi[i] = e - own_lo
+        d.push_dst[i] = peer_base[p] + inbox + buf * stride + (a - p_ext_lo) * 4
+    d.n_peer = len(peers)
+    for i, p in enumerate(peers):
+        d.peer_flag[i] = peer_base[p] + 4 * rank           # my slot in p's inbox
+        d.my_flag[i] = my_base + 4 * p                     # p's slot in mine
+    d.scratch = scratch_ptr
+    d.own_col_lo = own_lo - ext_lo; d.own_col_hi = own_hi - ext_lo
+    return d
+
+
 class PeerHalo:
     """Peer-mapped ping-pong x buffers + epoch inbox of one rank, and the bmsp_halo_desc of each buffer.
 
@@ -202,20 +222,9 @@ class PeerHalo:
             return None
         self.x = [_alias(self.base + cls.INBOX + b * stride, n_ext, "<f4", torch.float32, self) for b in range(cls.NBUF)]
         self.scratch = torch.zeros(4, dtype=torch.int32, device=sh.device)
-        self.desc = []
-        for b in range(cls.NBUF):
-            d = L.HaloDesc()
-            d.n_push = len(sh.send)
-            for i, (p, a, e) in enumerate(sh.send):
-                d.push_lo[i] = a - sh.own_lo; d.push_hi[i] = e - sh.own_lo
-                d.push_dst[i] = self.opened[p] + cls.INBOX + b * info[p]["stride"] + (a - info[p]["ext_lo"]) * 4
-            d.n_peer = len(peers)
-            for i, p in enumerate(peers):
-                d.peer_flag[i] = self.opened[p] + 4 * sh.rank
-                d.my_flag[i] = self.base + 4 * p
-            d.scratch = self.scratch.data_ptr()
-            d.own_col_lo = sh.own_lo - sh.ext_lo; d.own_col_hi = sh.own_hi - sh.ext_lo
-            self.desc.append(d)
+        self.desc = [halo_descriptor(b, sh.rank, sh.send, peers, sh.own_lo, sh.own_hi, sh.ext_lo, self.base, self.opened,
+                                     {p: (info[p]["stride"], info[p]["ext_lo"]) for p in peers}, self.scratch.data_ptr(), cls.INBOX)
+                     for b in range(cls.NBUF)]
         return self
 
     def first_push(self, sh):

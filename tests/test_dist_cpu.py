@@ -81,3 +81,43 @@ def test_split_by_weight():
     loads = [w[b[i]:b[i + 1]].sum() for i in range(4)]
     assert max(loads) <= 1.4 * sum(loads) / 4
     assert np.all(split_by_weight(np.ones(64), 8, align=8) % 8 == 0)
+
+
+def test_halo_descriptor_layout():
+    """The peer-memory halo plan (pure address arithmetic of dist.halo_descriptor): three slabs of a banded matrix.  Every push
+    range starts on a multiple of 4 rows, lands 16-byte aligned inside the peer's x buffer at the row's position in the peer's
+    extended range, and the epoch slots are mutual (my slot in the peer's inbox / the peer's slot in mine)."""
+    from bmsparse_spgemm_spmv_b200.dist import halo_descriptor
+    from bmsparse_spgemm_spmv_b200 import _lib as L
+    n, band = 3 * 4096, 64
+    bounds = [0, 4096, 8192, n]
+    ext = [(max(0, bounds[r] - band), min(n, bounds[r + 1] + band)) for r in range(3)]
+    base = {0: 0x10000000, 1: 0x20000000, 2: 0x30000000}
+    stride = {r: ((ext[r][1] - ext[r][0]) * 4 + 255) // 256 * 256 for r in range(3)}
+    descs = {}
+    for r in range(3):
+        own_lo, own_hi = bounds[r], bounds[r + 1]
+        send = []
+        for p in range(3):
+            if p != r:
+                a, e = max(ext[p][0], own_lo), min(ext[p][1], own_hi)
+                if a < e:
+                    send.append((p, a, e))
+        peers = sorted({p for p, _, _ in send})
+        for buf in range(3):
+            d = halo_descriptor(buf, r, send, peers, own_lo, own_hi, ext[r][0], base[r], base,
+                                {p: (stride[p], ext[p][0]) for p in peers}, 0x999000)
+            descs[(r, buf)] = (d, send, peers)
+            assert d.n_push == len(send) <= L.HALO_MAX and d.n_peer == len(peers)
+            assert d.own_col_lo == own_lo - ext[r][0] and d.own_col_hi == own_hi - ext[r][0]
+            for i, (p, a, e) in enumerate(send):
+                assert d.push_lo[i] % 4 == 0 and 0 <= d.push_lo[i] < d.push_hi[i] <= own_hi - own_lo
+                assert d.push_dst[i] % 16 == 0
+                # the destination is row `a` inside p's buffer `buf`
+                assert d.push_dst[i] == base[p] + 1024 + buf * stride[p] + (a - ext[p][0]) * 4
+                assert d.push_dst[i] + (e - a) * 4 <= base[p] + 1024 + (buf + 1) * stride[p]
+    # middle rank talks to both neighbours, the outer ranks to one; slots are mutual
+    assert descs[(1, 0)][2] == [0, 2] and descs[(0, 0)][2] == [1] and descs[(2, 0)][2] == [1]
+    d0, d1 = descs[(0, 1)][0], descs[(1, 1)][0]
+    assert d0.peer_flag[0] == base[1] + 4 * 0 and d1.my_flag[0] == base[1] + 4 * 0
+    assert d1.peer_flag[0] == base[0] + 4 * 1 and d0.my_flag[0] == base[0] + 4 * 1
