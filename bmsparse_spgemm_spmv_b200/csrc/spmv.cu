@@ -281,6 +281,18 @@ BMSP_ROWPAIR(float, __half, 1, BMSP_V32, BMSP_X16, "-32", "-48")
 #undef BMSP_X32
 #undef BMSP_X16
 
+template <typename V> __device__ __forceinline__ float lds_as_f32(uint32_t a);
+template <> __device__ __forceinline__ float lds_as_f32<float>(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+template <> __device__ __forceinline__ float lds_as_f32<__half>(uint32_t a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return __half2float(__ushort_as_half(v));
+}
+
 // The blocks of one block row seen by the thread that owns bitmap half h (rows 4h..4h+3).  Everything lives in
 // shared memory: bitmaps at a_bm, 16-bit x offsets at a_xo, the row's values from a_v on; xs31 = staged x + 31
 // elements.
@@ -298,7 +310,13 @@ __device__ __forceinline__ void tile_half_row(uint32_t a_bm, uint32_t a_xo, uint
         const uint32_t w = (w2.x & hm) | (w2.y & ~hm);
         const uint32_t va0 = a_v + (nhi & hm) * SV;
         a_v += (nhi + nlo) * SV;
-        if (w) {
+        if (w == (0x80402010u >> (4 * h))) {
+            // diagonal block (the +-m neighbours of a stencil, any band at a multiple of 8): row i of the half holds exactly
+            // column 4h + i -- four straight multiply-adds, no bit walk (20 instructions instead of ~50)
+            const uint32_t xa = xs31 - 31u * SX + (xo + 4u * (uint32_t)h) * SX;
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc[i] = fmaf(lds_as_f32<T>(va0 + i * SV), lds_as_f32<X>(xa + i * SX), acc[i]);
+        } else if (w) {
             const uint32_t xb = xs31 + xo * SX;
             const uint32_t b0 = w & 0xFF000000u, b1 = w & 0x00FF0000u, b2 = w & 0x0000FF00u, b3 = w & 0x000000FFu;
             const uint32_t va1 = va0 + __popc(b0) * SV, va2 = va1 + __popc(b1) * SV, va3 = va2 + __popc(b2) * SV;
