@@ -42,8 +42,6 @@ struct GemmArgs {
     const int32_t* row_list;   // when set: the rows to process, in this order (heavy-row / light-row launches); else row_begin + i
     int32_t n_list;
     int32_t batch;             // work items a CTA takes from the queue per atomic (tiny rows: the queue head would serialise the launch)
-    int32_t mma_list;          // NUMERIC_MMA: take the row's pairs from FILL's pair list (valid when FILL ran row by row) instead of
-                               // enumerating the candidates a third time
     int32_t split8;            // NUMERIC: 8 lanes per surviving pair, one per row of the A block (blocks with >= 4 values: a lane
                                // that multiplies a whole pair alone walks up to 64 x 8 dependent loads)
     int32_t group;             // consecutive block rows per work item (1..32): tiny rows are processed a group at a time -- one bit set, one
@@ -710,14 +708,11 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
                 // again rather than read from the pair list: FILL may have written the list a group of rows at a time
                 unsigned long long dc = 0, ds = 0;
                 enumerate_row<MODE_NUMERIC, false>(g, r, q, dc, ds);
-            } else if (g.mma_list) {
-                // FILL appended the survivors of one A block next to each other (runs of up to G lanes x 4 B blocks), which is
-                // what the two-pairs-per-MMA packing wants
-                PairMeta* stage = reinterpret_cast<PairMeta*>(q + 64);
-                for (uint32_t e0 = 0; e0 < nsurv; e0 += 32) drain_mma(g, r, list + e0, (int)min(32u, nsurv - e0), stage);
             } else {
                 unsigned long long dc = 0, ds = 0;
-                enumerate_row<MODE_MMA, false>(g, r, q, dc, ds);          // one warp per block row: pairs of an A block stay adjacent
+                // every warp enumerates its own A blocks, so the pairs of an A block stay adjacent in its queue (two B blocks per MMA);
+                // walking FILL's pair list instead of enumerating a third time measured no faster (BC4M 19.2 vs 18.6 ms)
+                enumerate_row<MODE_MMA, false>(g, r, q, dc, ds);
             }
             __syncthreads();
             if (PASS == PASS_NUMERIC && fit) for (int v = tid; v < rownnz; v += T) g.c_val[vbase + v] = s_acc[v];
@@ -1036,11 +1031,9 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
             if (max_c_row > g.cap_c) SG_CUDA(cudaMemsetAsync(C->values, 0, (size_t)c_nnz * 4, st));
             GemmArgs gm = g;
             gm.group = 1; gm.batch = avg_cand <= 96 ? 32 : 1;          // one warp per block row: pairs of an A block stay adjacent
-            { const char* e = getenv("BMSP_SPGEMM_MMA_LIST"); gm.mma_list = (group == 1 && !sp.active && (!e || atoi(e))) ? 1 : 0; }
             int Tm = 64;             // two warps per block row in the dense-block pass, sharing the row's accumulators (BC4M numeric, one box:
                                      // 32 threads 19.5 ms, 64: 17.7 ms, 128: 20.2 ms -- a row has ~10 A blocks x 4 lanes to hand out)
             if (const char* e = getenv("BMSP_SPGEMM_MMA_T")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) Tm = v; }
-            if (Tm > 32) gm.mma_list = 0;                               // the list walk is one warp's; more warps enumerate
             SG_TRY((launch_pass_t<PASS_NUMERIC_MMA, 256>(gm, Tm, sms, nrows, st)));
         } else {
             const double avg_nnz = nrows ? (double)c_nnz / nrows : 0.0;
