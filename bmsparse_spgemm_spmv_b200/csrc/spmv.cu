@@ -316,6 +316,14 @@ __device__ __forceinline__ void tile_half_row(uint32_t a_bm, uint32_t a_xo, uint
             const uint32_t xa = xs31 - 31u * SX + (xo + 4u * (uint32_t)h) * SX;
 #pragma unroll
             for (int i = 0; i < 4; i++) acc[i] = fmaf(lds_as_f32<T>(va0 + i * SV), lds_as_f32<X>(xa + i * SX), acc[i]);
+        } else if (w && !(w & (w - 1u))) {
+            // one value in this half (the +-1 neighbours of a stencil: a single cell in the whole block): one product, added to
+            // the row it belongs to
+            const uint32_t t = 31u - (uint32_t)(31 - __clz((int)w));          // = 8 * row + column
+            const float prod = lds_as_f32<T>(va0) * lds_as_f32<X>(xs31 - 31u * SX + (xo + (t & 7u)) * SX);
+            const uint32_t rr = t >> 3;
+            acc[0] += rr == 0u ? prod : 0.f; acc[1] += rr == 1u ? prod : 0.f;
+            acc[2] += rr == 2u ? prod : 0.f; acc[3] += rr == 3u ? prod : 0.f;
         } else if (w) {
             const uint32_t xb = xs31 + xo * SX;
             const uint32_t b0 = w & 0xFF000000u, b1 = w & 0x00FF0000u, b2 = w & 0x0000FF00u, b3 = w & 0x000000FFu;
