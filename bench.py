@@ -332,7 +332,7 @@ def main():
                      "frac_of_nominal_8TBs": nbytes / (kern_ms * 1e-3) / 1e9 / 8000.0,
                      "kernel": "spmv_tile_kernel<__half,float,64,2,12>", "kernel_ms": kern_ms},
         "e2e": {"value": total_bytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": ncols_local * 4, "d2h_bytes_per_step": nr * 4,
-                "ms_per_step": e2e_s * 1e3, "note": "bmsp_spmv_host: matrix resident in HBM (as in the reference's timed region); every step x comes from pinned host memory and y goes back to pinned host memory, chunked so that H2D, the row-range launches and D2H overlap (PCIe-bound)"},
+                "ms_per_step": e2e_s * 1e3, "note": "bmsp_spmv_host: matrix resident in HBM (as in the reference's timed region); every step x comes from pinned host memory in chunks on a copy stream while the row-range launches of the same kernel store y straight into the pinned host buffer (PCIe-bound both ways)"},
         "gpu_launches": K * launches_per_step,
         "clocks": clocks,
         "convert_ms": conv_ms,
