@@ -50,7 +50,7 @@ class HaloDesc(C.Structure):
 
 class SpgemmOpts(C.Structure):
     _fields_ = [("mode", C.c_int32), ("tc_version", C.c_int32), ("verbose", C.c_int32), ("numeric_path", C.c_int32),
-                ("brow_begin", C.c_int32), ("brow_end", C.c_int32)]
+                ("brow_begin", C.c_int32), ("brow_end", C.c_int32), ("brow_range_set", C.c_int32)]
 
 
 # every symbol include/bmsparse_b200.h declares (tests check the library exports each one)

@@ -44,6 +44,12 @@ struct bmsp_matrix_s {
     int32_t n_split_rows = 0;
     int32_t max_row_blocks = 0;
     void* host_pipe = nullptr;  // HostPipe (spmv.cu): streams, events and staging buffers of bmsp_spmv_host
+    // Stream ordering of the handle's memory: every entry point that enqueues work on the arrays records its stream here
+    // (bmsp::touch).  bmsp_destroy frees on that stream, so the frees are ordered behind the kernels that still read or write the
+    // arrays; a handle that was used on more than one stream is drained with a device synchronisation first.  Streams passed to
+    // calls on a matrix must outlive it.
+    cudaStream_t last_stream = nullptr;
+    bool multi_stream = false, touched = false;
 };
 
 namespace bmsp {
@@ -64,6 +70,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     } while (0)
 
 #define BMSP_KERNEL_CHECK() BMSP_CUDA(cudaGetLastError())
+
+// record that work on m's arrays was enqueued on st (see bmsp_matrix_s::last_stream)
+inline void touch(bmsp_matrix_s* m, cudaStream_t st) {
+    if (m->touched && m->last_stream != st) m->multi_stream = true;
+    m->last_stream = st; m->touched = true;
+}
 
 // stream-ordered allocation (+padding).  Freed with dev_free on the same stream.
 int dev_alloc(void** p, size_t bytes, cudaStream_t st);

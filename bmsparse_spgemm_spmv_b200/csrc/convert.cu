@@ -17,7 +17,20 @@
 
 namespace bmsp {
 
-enum { FLAG_UNSORTED = 1, FLAG_DUP = 2, FLAG_RANGE = 4 };
+enum { FLAG_UNSORTED = 1, FLAG_DUP = 2, FLAG_RANGE = 4, FLAG_ROWPTR = 8 };
+
+// row_ptr of a device CSR: starts at 0, ends at nnz, never decreases (rank_kernel binary-searches it and would read out of
+// bounds on anything else)
+__global__ void check_rowptr_kernel(const int32_t* __restrict__ rp, int32_t rows, int64_t nnz, int32_t* __restrict__ flags) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > rows) return;
+    const int32_t v = rp[r];
+    bool bad = v < 0 || (int64_t)v > nnz;
+    if (r == 0) bad |= v != 0;
+    if (r == rows) bad |= (int64_t)v != nnz;
+    else bad |= rp[r + 1] < v;
+    if (bad) atomicOr(flags, FLAG_ROWPTR);
+}
 
 __device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, int lo, int hi, int target) {
     while (lo < hi) {
@@ -168,6 +181,7 @@ static int convert_device_csr(int32_t rows, int32_t cols, int64_t nnz, const int
                               int vals_dtype, int transposed, int out_dtype, cudaStream_t st, bmsp_matrix_t* out) {
     if (nnz > 0xFFFFFFFFll) { set_error("nnz %lld exceeds 2^32-1", (long long)nnz); return BMSP_ERR_TOO_LARGE; }
     bmsp_matrix_s* m = new bmsp_matrix_s();
+    touch(m, st);
     m->rows = rows; m->cols = cols; m->nnz = nnz; m->dtype = out_dtype; m->transposed = transposed;
     uint64_t* s_key = nullptr; uint8_t* s_p = nullptr; int32_t* s_src = nullptr; int32_t* flags = nullptr;
     uint32_t* counts = nullptr;
@@ -178,13 +192,21 @@ static int convert_device_csr(int32_t rows, int32_t cols, int64_t nnz, const int
 #define CV_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return fail(cuda_fail(e__, #x, __FILE__, __LINE__)); } while (0)
     int64_t tiles = ceil_div(nnz, 1024);
     uint32_t nblk32 = 0;
+    CV_TRY(dev_alloc_t(&flags, 1, st));
+    CV_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t), st));
+    {
+        check_rowptr_kernel<<<(unsigned)ceil_div((int64_t)rows + 1, 256), 256, 0, st>>>(rp, rows, nnz, flags);
+        CV_CUDA(cudaGetLastError());
+        int32_t hflags = 0;
+        CV_CUDA(cudaMemcpyAsync(&hflags, flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CV_CUDA(cudaStreamSynchronize(st));
+        if (hflags & FLAG_ROWPTR) { set_error("row_ptr must start at 0, end at nnz and never decrease"); return fail(BMSP_ERR_INVALID); }
+    }
     if (nnz > 0) {
         CV_TRY(dev_alloc_t(&s_key, (size_t)nnz, st));
         CV_TRY(dev_alloc_t(&s_p, (size_t)nnz, st));
         CV_TRY(dev_alloc_t(&s_src, (size_t)nnz + 8, st));
-        CV_TRY(dev_alloc_t(&flags, 1, st));
         CV_TRY(dev_alloc_t(&counts, (size_t)tiles + 1, st));
-        CV_CUDA(cudaMemsetAsync(flags, 0, sizeof(int32_t), st));
         unsigned grid = (unsigned)ceil_div(nnz, 256);
         if (transposed) rank_kernel<true><<<grid, 256, 0, st>>>(rp, ci, rows, cols, nnz, s_key, s_p, s_src, flags);
         else            rank_kernel<false><<<grid, 256, 0, st>>>(rp, ci, rows, cols, nnz, s_key, s_p, s_src, flags);
@@ -360,7 +382,9 @@ int bmsp_create_from_mtx(const char* path, int32_t transposed, int32_t out_dtype
 int bmsp_block_transpose(bmsp_matrix_t A, int32_t out_dtype, void* stream, bmsp_matrix_t* At) {
     if (!A || !At || (out_dtype != BMSP_F16 && out_dtype != BMSP_F32)) { set_error("bmsp_block_transpose: invalid argument"); return BMSP_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    touch(A, st);
     bmsp_matrix_s* m = new bmsp_matrix_s();
+    touch(m, st);
     m->rows = A->rows; m->cols = A->cols; m->nnz = A->nnz; m->nblk = A->nblk; m->offsets_len = A->offsets_len;
     m->dtype = out_dtype; m->transposed = !A->transposed;
     int s;
@@ -370,14 +394,16 @@ int bmsp_block_transpose(bmsp_matrix_t A, int32_t out_dtype, void* stream, bmsp_
     if ((s = dev_alloc_t(&m->offsets, (size_t)m->nblk + 2, st))) return fail(s);
     if ((s = dev_alloc(&m->values, (size_t)m->nnz * dsize(out_dtype) + 16, st))) return fail(s);
     if (m->nblk) {
-        cudaMemcpyAsync(m->keys, A->keys, sizeof(uint64_t) * m->nblk, cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(m->offsets, A->offsets, sizeof(uint64_t) * m->offsets_len, cudaMemcpyDeviceToDevice, st);
+        cudaError_t ce = cudaMemcpyAsync(m->keys, A->keys, sizeof(uint64_t) * m->nblk, cudaMemcpyDeviceToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(m->offsets, A->offsets, sizeof(uint64_t) * m->offsets_len, cudaMemcpyDeviceToDevice, st);
+        if (ce != cudaSuccess) return fail(cuda_fail(ce, "block_transpose: copy keys/offsets", __FILE__, __LINE__));
         unsigned grid = (unsigned)ceil_div(m->nblk, 128);
         if (A->dtype == BMSP_F16 && out_dtype == BMSP_F16) block_transpose_kernel<__half, __half><<<grid, 128, 0, st>>>(A->bmps, A->offsets, (const __half*)A->values, m->bmps, (__half*)m->values, m->nblk);
         else if (A->dtype == BMSP_F32 && out_dtype == BMSP_F16) block_transpose_kernel<float, __half><<<grid, 128, 0, st>>>(A->bmps, A->offsets, (const float*)A->values, m->bmps, (__half*)m->values, m->nblk);
         else if (A->dtype == BMSP_F32 && out_dtype == BMSP_F32) block_transpose_kernel<float, float><<<grid, 128, 0, st>>>(A->bmps, A->offsets, (const float*)A->values, m->bmps, (float*)m->values, m->nblk);
         else block_transpose_kernel<__half, float><<<grid, 128, 0, st>>>(A->bmps, A->offsets, (const __half*)A->values, m->bmps, (float*)m->values, m->nblk);
-        if (cudaGetLastError() != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "block_transpose", __FILE__, __LINE__));
+        ce = cudaGetLastError();
+        if (ce != cudaSuccess) return fail(cuda_fail(ce, "block_transpose", __FILE__, __LINE__));
     }
     if ((s = derive_compact(m, st))) return fail(s);
     *At = m;

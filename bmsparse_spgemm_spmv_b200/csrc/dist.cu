@@ -50,6 +50,8 @@ extern "C" int bmsp_partition_block_rows(bmsp_matrix_t A, bmsp_matrix_t Bt, int3
     if (!A || !bounds || nparts < 1 || (weight_spgemm && !Bt)) { set_error("bmsp_partition_block_rows: invalid argument"); return BMSP_ERR_INVALID; }
     if (weight_spgemm && A->cols != Bt->rows) { set_error("bmsp_partition_block_rows: inner dimensions differ"); return BMSP_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    touch(A, st);
+    if (Bt) touch(Bt, st);
     const int nbr = A->nbr;
     bounds[0] = 0; bounds[nparts] = nbr;
     if (nbr == 0) { for (int p = 1; p < nparts; p++) bounds[p] = 0; return BMSP_OK; }
@@ -78,6 +80,7 @@ extern "C" int bmsp_partition_block_rows(bmsp_matrix_t A, bmsp_matrix_t Bt, int3
 extern "C" int bmsp_slice_block_rows(bmsp_matrix_t A, int32_t r0, int32_t r1, int32_t rebase_rows, void* stream, bmsp_matrix_t* out) {
     if (!A || !out || r0 < 0 || r1 > A->nbr || r0 > r1) { set_error("bmsp_slice_block_rows: invalid argument"); return BMSP_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    touch(A, st);
     int32_t hb[2] = {0, 0}; uint32_t hv[2] = {0, 0};
     BMSP_CUDA(cudaMemcpyAsync(&hb[0], A->brp + r0, 4, cudaMemcpyDeviceToHost, st));
     BMSP_CUDA(cudaMemcpyAsync(&hb[1], A->brp + r1, 4, cudaMemcpyDeviceToHost, st));
@@ -87,6 +90,7 @@ extern "C" int bmsp_slice_block_rows(bmsp_matrix_t A, int32_t r0, int32_t r1, in
     const int64_t nblk = hb[1] - hb[0], nnz = (int64_t)hv[1] - hv[0];
     const size_t vs = A->dtype == BMSP_F16 ? 2 : 4;
     bmsp_matrix_s* m = new bmsp_matrix_s();
+    touch(m, st);
     m->cols = A->cols; m->dtype = A->dtype; m->transposed = A->transposed;
     m->rows = rebase_rows ? std::min<int64_t>((int64_t)(r1 - r0) * 8, (int64_t)A->rows - (int64_t)r0 * 8) : A->rows;
     if (m->rows < 0) m->rows = 0;
@@ -98,12 +102,14 @@ extern "C" int bmsp_slice_block_rows(bmsp_matrix_t A, int32_t r0, int32_t r1, in
     if ((s = dev_alloc_t(&m->offsets, (size_t)nblk + 2, st))) return fail(s);
     if ((s = dev_alloc(&m->values, (size_t)nnz * vs + 16, st))) return fail(s);
     if (nblk) {
-        cudaMemcpyAsync(m->keys, A->keys + hb[0], 8 * nblk, cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(m->bmps, A->bmps + hb[0], 8 * nblk, cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(m->offsets, A->offsets + hb[0], 8 * nblk, cudaMemcpyDeviceToDevice, st);
-        if (nnz) cudaMemcpyAsync(m->values, (const char*)A->values + (size_t)hv[0] * vs, (size_t)nnz * vs, cudaMemcpyDeviceToDevice, st);
+        cudaError_t ce = cudaMemcpyAsync(m->keys, A->keys + hb[0], 8 * nblk, cudaMemcpyDeviceToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(m->bmps, A->bmps + hb[0], 8 * nblk, cudaMemcpyDeviceToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(m->offsets, A->offsets + hb[0], 8 * nblk, cudaMemcpyDeviceToDevice, st);
+        if (ce == cudaSuccess && nnz) ce = cudaMemcpyAsync(m->values, (const char*)A->values + (size_t)hv[0] * vs, (size_t)nnz * vs, cudaMemcpyDeviceToDevice, st);
+        if (ce != cudaSuccess) return fail(cuda_fail(ce, "slice: copy arrays", __FILE__, __LINE__));
         slice_rebase_kernel<<<(unsigned)ceil_div(nblk, 256), 256, 0, st>>>(m->keys, m->offsets, nblk, nblk, rebase_rows ? (uint64_t)r0 : 0, hv[0]);
-        if (cudaGetLastError() != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "slice", __FILE__, __LINE__));
+        ce = cudaGetLastError();
+        if (ce != cudaSuccess) return fail(cuda_fail(ce, "slice", __FILE__, __LINE__));
     }
     if ((s = derive_compact(m, st))) return fail(s);
     *out = m;

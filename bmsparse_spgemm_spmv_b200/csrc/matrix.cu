@@ -224,6 +224,7 @@ int bmsp_create_from_arrays(int32_t rows, int32_t cols, int64_t block_num, int64
     }
     cudaStream_t st = (cudaStream_t)stream;
     bmsp_matrix_s* m = new bmsp_matrix_s();
+    touch(m, st);
     m->rows = rows; m->cols = cols; m->nblk = block_num; m->nnz = nnz; m->offsets_len = offsets_len;
     m->dtype = dtype; m->transposed = transposed;
     cudaMemcpyKind kind = mem == BMSP_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
@@ -250,7 +251,9 @@ int bmsp_create_from_arrays(int32_t rows, int32_t cols, int64_t block_num, int64
 
 int bmsp_destroy(bmsp_matrix_t m) {
     if (!m) return BMSP_OK;
-    cudaStream_t st = 0;
+    // frees are ordered behind the last work enqueued on the arrays (stream 0 does not order after non-blocking streams)
+    if (m->multi_stream) cudaDeviceSynchronize();
+    cudaStream_t st = m->last_stream;
     spmv_host_release(m);
     dev_free(m->keys, st); dev_free(m->bmps, st); dev_free(m->offsets, st); dev_free(m->values, st);
     dev_free(m->brp, st); dev_free(m->bcol, st); dev_free(m->rvb, st); dev_free(m->kmask, st);
@@ -307,7 +310,8 @@ __global__ void to_coo_kernel(const uint64_t* __restrict__ keys, const uint64_t*
 extern "C" int bmsp_to_coo(bmsp_matrix_t m, int32_t* rows, int32_t* cols, float* vals) {
     if (!m || !rows || !cols || !vals) { set_error("bmsp_to_coo: null argument"); return BMSP_ERR_INVALID; }
     if (m->nnz == 0) return BMSP_OK;
-    cudaStream_t st = 0;
+    if (m->multi_stream) BMSP_CUDA(cudaDeviceSynchronize());
+    cudaStream_t st = m->last_stream;          // ordered behind whatever produced the arrays
     int32_t *dr = nullptr, *dc = nullptr; float* dv = nullptr;
     BMSP_TRY(dev_alloc_t(&dr, (size_t)m->nnz, st));
     BMSP_TRY(dev_alloc_t(&dc, (size_t)m->nnz, st));

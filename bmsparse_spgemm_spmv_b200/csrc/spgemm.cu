@@ -834,8 +834,11 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     if (A->dtype != BMSP_F16 || Bt->dtype != BMSP_F16) { set_error("bmsp_spgemm: operands must be fp16 (bmSparse_mult<half,float>)"); return BMSP_ERR_UNSUPPORTED; }
     if (A->cols != Bt->rows) { set_error("bmsp_spgemm: inner dimensions differ (%d vs %d)", A->cols, Bt->rows); return BMSP_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    touch(A, st); touch(Bt, st);
     int rb = 0, re = A->nbr;
-    if (opts && (opts->brow_begin != 0 || opts->brow_end != 0)) { rb = opts->brow_begin; re = opts->brow_end; }
+    // brow_range_set: the range is taken literally ([r, r) multiplies nothing: a shard that owns no rows); without it the legacy
+    // rule applies -- [0, 0) means all rows
+    if (opts && (opts->brow_range_set || opts->brow_begin != 0 || opts->brow_end != 0)) { rb = opts->brow_begin; re = opts->brow_end; }
     if (rb < 0 || re > A->nbr || rb > re) { set_error("bmsp_spgemm: bad block-row range [%d,%d)", rb, re); return BMSP_ERR_INVALID; }
     const int nrows = re - rb;
     const bool verbose = opts && opts->verbose;
@@ -852,6 +855,7 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     int2* rowinfo = nullptr; unsigned long long* cand = nullptr; int32_t* small = nullptr;   // small: maxes[3], counter, pad, stats[2]
     uint32_t *row_count = nullptr, *row_surv = nullptr; uint64_t* row_nnz = nullptr; uint2* surv_list = nullptr;
     bmsp_matrix_s* C = new bmsp_matrix_s();
+    touch(C, st);
     C->rows = A->rows; C->cols = Bt->cols; C->dtype = BMSP_F32; C->transposed = 0;
     C->nbr = (int32_t)ceil_div(C->rows, 8);
     uint32_t *g_bitset = nullptr, *g_wrank = nullptr;

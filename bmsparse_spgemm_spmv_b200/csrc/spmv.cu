@@ -521,10 +521,16 @@ __global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileAr
         if (n2) bulk_g2s(smem + a.so.xo, a.xoff + p0x, n2, bar);
         if (nvb) bulk_g2s(smem + a.so.val, a.values + v0a, nvb, bar);
     }
+    bool part = false;               // DIST: this tile owns rows a peer needs (CTA-uniform)
     if constexpr (DIST) {
-        // Only a tile whose x lines leave this rank's own columns depends on the peers.  The matrix copies above are already
-        // in flight; x must not be touched before the halo is in.
-        if (nb > 0 && ((int64_t)d1.z * 32 < hd.own_c0 || ((int64_t)d1.w + 1) * 32 > hd.own_c1)) {
+        const int trow0 = r0 * 8, trow1 = min(a.rows, (r0 + nrow) * 8);
+        part = t == hd.solo_tile;
+        for (int i = 0; i < hd.n_push; i++) part |= hd.lo[i] < trow1 && hd.hi[i] > trow0;
+        // A tile depends on the peers when its x lines leave this rank's own columns (it reads rows they pushed) or when it
+        // pushes rows itself: the peers' epoch is the back-pressure that keeps this rank from overwriting a buffer a slower
+        // peer still reads, also for one-directional patterns (triangular, directed graphs) where a pushing tile reads nothing
+        // remote.  The matrix copies above are already in flight; x must not be touched before the halo is in.
+        if (part || (nb > 0 && ((int64_t)d1.z * 32 < hd.own_c0 || ((int64_t)d1.w + 1) * 32 > hd.own_c1))) {
             if (tid < hd.n_peer) halo_wait(hd, tid);
             __syncthreads();
         }
@@ -601,10 +607,6 @@ __global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileAr
         }
     }
     if constexpr (DIST) {
-        // does this tile own rows a peer needs?  (CTA-uniform)
-        const int trow0 = r0 * 8, trow1 = min(a.rows, (r0 + nrow) * 8);
-        bool part = t == hd.solo_tile;
-        for (int i = 0; i < hd.n_push; i++) part |= hd.lo[i] < trow1 && hd.hi[i] > trow0;
         if (part) {
             if (active) halo_store<NR>(hd, row, a.rows, acc);
             __threadfence_system();
@@ -944,7 +946,9 @@ static int host_pipe_get(bmsp_matrix_s* A, cudaStream_t st, HostPipe** out) {
         }
         hp->tile_lo.push_back(ntiles);
     } else {
-        hp->tile_lo = {0, 0};
+        // one chunk: all tiles of a row-tiled matrix ({0, 0} launched nothing and left y_host untouched); the
+        // block-parallel path ignores tile_lo
+        hp->tile_lo = {0, A->spmv_path == 0 ? (int)ceil_div(A->nbr, A->tile_rows) : 0};
         hp->x_need = {(int64_t)A->cols};
     }
     hp->nchunks = (int)hp->x_need.size();
@@ -966,7 +970,7 @@ void spmv_host_release(bmsp_matrix_s* m) {
     if (hp->ev_done) cudaEventDestroy(hp->ev_done);
     for (auto e : hp->ev_x) if (e) cudaEventDestroy(e);
     for (auto e : hp->ev_k) if (e) cudaEventDestroy(e);
-    dev_free(hp->x_dev, 0); dev_free(hp->y_dev, 0);
+    dev_free(hp->x_dev, m->last_stream); dev_free(hp->y_dev, m->last_stream);     // the product kernels ran on the caller's stream
     delete hp;
     m->host_pipe = nullptr;
 }
@@ -1066,6 +1070,7 @@ extern "C" int bmsp_spmv_host(bmsp_matrix_t A, const void* x_host, int32_t x_dty
     if (A->transposed) { set_error("bmsp_spmv_host: matrix is in transposed-operand form"); return BMSP_ERR_UNSUPPORTED; }
     if (A->rows == 0) return BMSP_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    touch(A, st);
     if (A->spmv_path < 0) BMSP_TRY(plan_spmv(A, st));
     HostPipe* hp = nullptr;
     BMSP_TRY(host_pipe_get(A, st, &hp));
@@ -1084,13 +1089,15 @@ static int halo_to_dev(const bmsp_halo_desc* d, int rows, HaloDev* h) {
         set_error("halo descriptor: bad counts or missing scratch"); return BMSP_ERR_INVALID;
     }
     memset(h, 0, sizeof(*h));
-    h->n_push = d->n_push; h->n_peer = d->n_peer; h->scratch = (uint32_t*)d->scratch; h->solo_tile = -1;
+    h->n_push = 0; h->n_peer = d->n_peer; h->scratch = (uint32_t*)d->scratch; h->solo_tile = -1;
     h->own_c0 = d->own_col_lo; h->own_c1 = d->own_col_hi;
     for (int i = 0; i < d->n_push; i++) {
         if (d->push_lo[i] < 0 || d->push_hi[i] > rows || d->push_lo[i] > d->push_hi[i] || (d->push_lo[i] & 3) || ((uintptr_t)d->push_dst[i] & 15)) {
             set_error("halo descriptor: push range %d [%d,%d) invalid or misaligned", i, d->push_lo[i], d->push_hi[i]); return BMSP_ERR_INVALID;
         }
-        h->lo[i] = d->push_lo[i]; h->hi[i] = d->push_hi[i]; h->dst[i] = (float*)d->push_dst[i];
+        if (d->push_lo[i] == d->push_hi[i]) continue;      // an empty range pushes nothing and must not count as a signalling tile
+        const int k = h->n_push++;
+        h->lo[k] = d->push_lo[i]; h->hi[k] = d->push_hi[i]; h->dst[k] = (float*)d->push_dst[i];
     }
     for (int i = 0; i < d->n_peer; i++) { h->peer_flag[i] = (uint32_t*)d->peer_flag[i]; h->my_flag[i] = (const uint32_t*)d->my_flag[i]; }
     return BMSP_OK;
@@ -1130,6 +1137,7 @@ extern "C" int bmsp_spmv_halo(bmsp_matrix_t A, const float* x_ext, float* y_own,
     if (A->transposed) { set_error("bmsp_spmv_halo: matrix is in transposed-operand form"); return BMSP_ERR_UNSUPPORTED; }
     if (((uintptr_t)x_ext & 15) || ((uintptr_t)y_own & 15)) { set_error("bmsp_spmv_halo: x and y must be 16-byte aligned"); return BMSP_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    touch(A, st);
     HaloDev h;
     BMSP_TRY(halo_to_dev(halo, A->rows, &h));
     h.wait_epoch = wait_epoch; h.signal_epoch = signal_epoch;
@@ -1192,6 +1200,7 @@ extern "C" int bmsp_spmv(bmsp_matrix_t A, const void* x, int32_t x_dtype, float*
     if (A->rows == 0) return BMSP_OK;
     if (((uintptr_t)x & 15) || ((uintptr_t)y & 15)) { set_error("bmsp_spmv: x and y must be 16-byte aligned"); return BMSP_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    touch(A, st);
     if (A->spmv_path < 0) BMSP_TRY(plan_spmv(A, st));
     if (A->dtype == BMSP_F16)
         return x_dtype == BMSP_F32 ? launch_spmv<__half, float>(A, (const float*)x, y, st) : launch_spmv<__half, __half>(A, (const __half*)x, y, st);

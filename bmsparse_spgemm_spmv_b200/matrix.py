@@ -54,7 +54,7 @@ class bmSpMatrix:
             L.check(L.lib().bmsp_create_from_csr(int(num_rows), int(num_cols), C.c_int64(ci.numel()), C.c_void_p(rp.data_ptr()),
                                                  C.c_void_p(ci.data_ptr()), C.c_void_p(v.data_ptr()), _dt(v.dtype), L.DEVICE,
                                                  int(transpose), _dt(dtype), _stream_ptr(stream), C.byref(m._h)))
-            torch.cuda.current_stream().synchronize()
+            (stream if stream is not None else torch.cuda.current_stream()).synchronize()      # rp / ci / v temporaries die here
         else:
             rp = np.ascontiguousarray(row_ptr, np.int32); ci = np.ascontiguousarray(col_idx, np.int32)
             v = np.ascontiguousarray(vals)

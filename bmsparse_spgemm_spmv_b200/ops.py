@@ -48,7 +48,8 @@ def bmSparse_mult(A: bmSpMatrix, B: bmSpMatrix, C_out: bmSpMatrix | None = None,
     """C = A * B with B in transposed-operand form (built with transpose=True, SPGEMM.cu:1262).
     Returns (C, info).  `mode` / `tc_version` are accepted for drop-in compatibility and ignored."""
     opts = L.SpgemmOpts(int(mode), int(tc_version), int(bool(VERBOSE)), int(numeric_path),
-                        brow_range[0] if brow_range else 0, brow_range[1] if brow_range else 0)
+                        brow_range[0] if brow_range is not None else 0, brow_range[1] if brow_range is not None else 0,
+                        int(brow_range is not None))
     info = L.SpgemmInfo()
     out = C_out if C_out is not None else bmSpMatrix()
     if out._h:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BMSP_ABI_VERSION 1
+#define BMSP_ABI_VERSION 2
 
 typedef enum {
     BMSP_OK = 0,
@@ -80,7 +80,9 @@ typedef struct {
     int32_t tc_version;   /* accepted and ignored: multiplyV11..V15 selector (SPGEMM.cu:1132-1154)  */
     int32_t verbose;      /* 1: fill bmsp_spgemm_info with per-phase times (costs event syncs)      */
     int32_t numeric_path; /* -1 auto, 0 force scalar, 1 force mma.sync                              */
-    int32_t brow_begin, brow_end;  /* A block-row range to multiply ([0,0) = all): multi-GPU shard  */
+    int32_t brow_begin, brow_end;  /* A block-row range to multiply: multi-GPU shard / chunked product */
+    int32_t brow_range_set;        /* 1: [brow_begin, brow_end) is taken literally (an empty range multiplies nothing);
+                                      0: legacy rule, [0,0) = all block rows                                     */
 } bmsp_spgemm_opts;
 
 /* ---- library ------------------------------------------------------------------------------- */

@@ -57,8 +57,42 @@ def main():
         assert np.isfinite(scale) and err < 1e-4, f"{name}: rank {rank} rel err {err} (scale {scale})"
         if rank == 0:
             print(f"DIST_OK {name} world={world} rows={n} err={err:.2e}", flush=True)
+    one_directional(rank, world, dev)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def one_directional(rank, world, dev):
+    """lower-bidiagonal matrix -- rank r pushes its last row to rank r+1 and reads nothing remote, so only the epoch
+    wait of the pushing tile keeps it from running products ahead of a slow reader and overwriting a buffer still in use.
+    Many steps, the last rank deliberately slowed; the result must equal the single-GPU iteration."""
+    n = 4096 * world
+    i = np.arange(n, dtype=np.int64)
+    cols = np.stack([i - 1, i], axis=1); valid = np.stack([i > 0, np.ones(n, bool)], axis=1)
+    ci = cols[valid].astype(np.int32); v = np.full(ci.size, 0.5, np.float32)
+    rp = np.zeros(n + 1, np.int64); np.cumsum(valid.sum(1), out=rp[1:])
+    bounds = np.arange(world + 1, dtype=np.int64) * 4096
+    lcsr = csr_row_slice(rp.astype(np.int32), ci, v, int(bounds[rank]), int(bounds[rank + 1]))
+    x0 = G.x_vector(n)
+    steps = 120
+    sh = ShardedSpMV(bounds, lcsr, n, device=dev, halo="p2p")
+    assert sh.local.nnz / sh.local.block_num >= 2.5            # row-tiled path: the fused kernel
+    sh.set_x(torch.from_numpy(x0[bounds[rank]:bounds[rank + 1]]).to(dev))
+    for _ in range(steps):
+        if rank == world - 1:
+            torch.cuda._sleep(400000)                          # ~0.2 ms: the reader falls behind
+        sh.step()
+    torch.cuda.synchronize()
+    sh.check()
+    got = sh.y_own().clone()
+    sh.close()
+    A = B.bmSpMatrix.from_csr(n, n, rp.astype(np.int32), ci, v)
+    x = torch.from_numpy(x0).to(dev)
+    for _ in range(steps):
+        x = B.bmSparse_SpMV(A, x)
+    assert torch.equal(got, x[bounds[rank]:bounds[rank + 1]]), f"one-directional: rank {rank} differs from the single-GPU iteration"
+    if rank == 0:
+        print(f"DIST_OK one_directional world={world} steps={steps}", flush=True)
 
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/bmsparse_b200.h but not exported"
     assert sorted(_lib.SYMBOLS) == names
     lib.bmsp_abi_version.restype = ctypes.c_int
-    assert lib.bmsp_abi_version() == 1
+    assert lib.bmsp_abi_version() == 2
 
 
 def test_no_oracle_import_in_product():

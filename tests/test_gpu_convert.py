@@ -134,3 +134,18 @@ def test_from_arrays_and_block_transpose(B, oracle):
     sel = (A.keys >> np.uint64(32) >= 3) & (A.keys >> np.uint64(32) < 11)
     assert np.array_equal(ks, A.keys[sel]) and np.array_equal(bs, A.bmps[sel])
     assert np.array_equal(os_, A.offsets[sel] - A.offsets[sel][0])
+
+
+def test_device_csr_row_ptr_is_validated(B):
+    """a device CSR with a bad row_ptr must be rejected, not binary-searched out of bounds."""
+    import bmsparse_spgemm_spmv_b200._lib as L
+    nr, nc = 64, 64
+    ci = torch.arange(64, dtype=torch.int32, device="cuda"); v = torch.ones(64, device="cuda")
+    good = torch.arange(65, dtype=torch.int32, device="cuda")
+    assert B.bmSpMatrix.from_csr(nr, nc, good, ci, v).nnz == 64
+    swapped = good.clone(); swapped[10], swapped[11] = good[11].item(), good[10].item()      # decreases once
+    short = good.clone(); short[-1] = 63                                                       # does not end at nnz
+    for bad in (good + 1, swapped, short, -good):
+        with pytest.raises(L.BmspError) as e:
+            B.bmSpMatrix.from_csr(nr, nc, bad, ci, v)
+        assert e.value.code == 1

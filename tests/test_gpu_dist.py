@@ -24,5 +24,5 @@ def test_sharded_spmv_peer_memory(world):
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dist_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    for name in ("poisson", "clustered", "rmat", "uniform"):
+    for name in ("poisson", "clustered", "rmat", "uniform", "one_directional"):
         assert f"DIST_OK {name}" in r.stdout, r.stdout[-2000:]

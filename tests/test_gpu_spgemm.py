@@ -198,3 +198,17 @@ def test_full_size_u1m_properties(B):
     y2 = B.bmSparse_SpMV(C, x)
     tol = 1e-4 * float(y1.abs().max())
     assert float((y1 - y2).abs().max()) <= tol
+
+
+def test_empty_block_row_range_multiplies_nothing(B):
+    """brow_range=(0, 0) -- a shard that owns no block rows -- used to mean "all rows"."""
+    G = B.generators
+    nr, nc, rp, ci, v = G.poisson5pt(48, 40)
+    A = B.bmSpMatrix.from_csr(nr, nc, rp, ci, v); Bt = B.bmSpMatrix.from_csr(nr, nc, rp, ci, v, transpose=True)
+    full, _ = B.bmSparse_mult(A, Bt)
+    for rng_ in ((0, 0), (5, 5), (A.num_block_rows, A.num_block_rows)):
+        C, info = B.bmSparse_mult(A, Bt, brow_range=rng_)
+        assert C.block_num == 0 and C.nnz == 0 and info.c_blocks == 0
+        assert C.download()[2].tolist() == [0]
+    C, _ = B.bmSparse_mult(A, Bt, brow_range=None)
+    assert C.block_num == full.block_num > 0
