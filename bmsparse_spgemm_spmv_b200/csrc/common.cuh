@@ -32,6 +32,8 @@ struct bmsp_matrix_s {
     int32_t cap_blk = 0, cap_val = 0;   // per-tile smem capacities of the row-tiled kernels
     int32_t cap_lines = 0;      // staged x lines per tile (tile plan)
     int32_t tile_rows = 64;     // block rows per tile (64, 32 or 16)
+    int32_t spmv_kernel = 0;    // row-tiled path: 0 = streaming kernel (persistent CTAs, staged tiles in a shared-memory ring), 1 = one CTA per tile
+    int32_t xl_pitch = 32;      // elements between staged x lines (32 for the streaming kernel's bulk copies, 33 for the per-tile kernel)
     void* tile_rowpair = nullptr;   // [nbr+1] int2 (block_row_ptr, first value) zipped for one bulk copy per tile
     void* tile_desc = nullptr;  // [ntiles] TileDesc (spmv.cu): block / value / x-line ranges of every tile of 64 block rows
     uint32_t* tile_lines = nullptr;   // [nblk] distinct x lines (32 columns) of every tile, stored from the tile's first block index
@@ -123,6 +125,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(

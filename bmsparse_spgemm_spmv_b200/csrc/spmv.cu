@@ -108,10 +108,14 @@ constexpr int XL_STRIDE = 33;      // staged x line pitch, elements (32 + 1 skew
 constexpr int PLAN_MAXB = 2048;    // blocks per tile the planner sorts in shared memory
 constexpr int XL_MAX = 1900;       // distinct lines per tile (16-bit element offsets)
 
-struct __align__(16) TileDesc { int32_t p0, nb; uint32_t v0; int32_t nv, nl, flags, lmin, lmax; };   // 32 bytes; [lmin, lmax] = x lines touched
+// 64 bytes; [lmin, lmax] = x lines touched.  The distinct lines of a stencil / band / cluster tile form a few runs of consecutive
+// lines: up to three runs (first line, line count) are kept in the descriptor so that the streaming kernel can fetch the tile's
+// x with one bulk copy per run without reading the line list (nruns = 0: more than three runs, copy line by line).
+struct __align__(16) TileDesc { int32_t p0, nb; uint32_t v0; int32_t nv, nl, flags, lmin, lmax; int32_t nruns; uint32_t run_line[3], run_count[3]; int32_t pad; };
+static_assert(sizeof(TileDesc) == 64, "TileDesc is four 16-byte words");
 
 __global__ void __launch_bounds__(256) tile_plan_kernel(const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
-                                                        const uint32_t* __restrict__ rvb, int nbr, int ncols, int rt, TileDesc* __restrict__ desc,
+                                                        const uint32_t* __restrict__ rvb, int nbr, int ncols, int rt, int pitch, TileDesc* __restrict__ desc,
                                                         uint32_t* __restrict__ lines, uint16_t* __restrict__ xoff,
                                                         unsigned long long* __restrict__ stats) {
     __shared__ uint32_t s_key[PLAN_MAXB];
@@ -123,6 +127,8 @@ __global__ void __launch_bounds__(256) tile_plan_kernel(const int32_t* __restric
     const uint32_t v0 = rvb[r0], v1 = rvb[r1];
     TileDesc d;
     d.p0 = p0; d.nb = nb; d.v0 = v0; d.nv = (int32_t)(v1 - v0); d.nl = 0; d.flags = 0; d.lmin = 0; d.lmax = nb > 0 ? 0x7FFFFFFF : -1;
+    d.nruns = 0; d.pad = 0;
+    for (int k = 0; k < 3; k++) { d.run_line[k] = 0; d.run_count[k] = 0; }
     if (nb > PLAN_MAXB) {          // too many blocks to plan: the kernel reads this tile straight from global memory
         if (tid == 0) { desc[t] = d; atomicAdd(stats + 4, 1ull); }
         return;
@@ -176,12 +182,19 @@ __global__ void __launch_bounds__(256) tile_plan_kernel(const int32_t* __restric
                 const int mid = (lo + hi) >> 1;
                 if (s_uniq[mid] < line) lo = mid + 1; else hi = mid;
             }
-            xoff[p0 + i] = (uint16_t)(lo * XL_STRIDE + (int)(c & 3u) * 8);
+            xoff[p0 + i] = (uint16_t)(lo * pitch + (int)(c & 3u) * 8);
         }
     if (tid == 0) {
         // flags: bit 0 = planned (x offsets valid), bit 1 = the last line reaches past the last column (guarded gather)
         if (nb > 0) { d.lmin = (int32_t)s_uniq[0]; d.lmax = (int32_t)s_uniq[nl - 1]; }
         d.nl = nl; d.flags = (ok ? 1 : 0) | ((nl > 0 && (uint64_t)s_uniq[nl - 1] * 32u + 32u > (uint64_t)ncols) ? 2 : 0);
+        // runs of consecutive lines (at most three are kept; a fourth makes the tile a line-by-line one)
+        int nruns = 0;
+        for (int j = 0; j < nl && nruns <= 3; j++) {
+            if (j == 0 || s_uniq[j] != s_uniq[j - 1] + 1u) { if (nruns < 3) { d.run_line[nruns] = s_uniq[j]; d.run_count[nruns] = 0; } nruns++; }
+            if (nruns <= 3) d.run_count[nruns - 1]++;
+        }
+        d.nruns = nruns <= 3 ? nruns : 0;
         desc[t] = d;
         atomicMax(stats + 0, (unsigned long long)nb);
         atomicMax(stats + 1, (unsigned long long)(v1 - v0));
@@ -296,7 +309,19 @@ template <> __device__ __forceinline__ float lds_as_f32<__half>(uint32_t a) {
 // The blocks of one block row seen by the thread that owns bitmap half h (rows 4h..4h+3).  Everything lives in
 // shared memory: bitmaps at a_bm, 16-bit x offsets at a_xo, the row's values from a_v on; xs31 = staged x + 31
 // elements.
-template <typename T, typename X>
+template <typename X> __device__ __forceinline__ void lds_x4(uint32_t a, float (&o)[4]);
+template <> __device__ __forceinline__ void lds_x4<float>(uint32_t a, float (&o)[4]) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(a));
+}
+template <> __device__ __forceinline__ void lds_x4<__half>(uint32_t a, float (&o)[4]) {
+    uint32_t lo, hi;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a));
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&lo)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    o[0] = f0.x; o[1] = f0.y; o[2] = f1.x; o[3] = f1.y;
+}
+
+// XV: the staged x lines are dense (pitch 32) and 16-byte aligned, so the four x elements of a bitmap half are one vector load
+template <typename T, typename X, bool XV = false>
 __device__ __forceinline__ void tile_half_row(uint32_t a_bm, uint32_t a_xo, uint32_t a_v, int nb, const int h, const uint32_t xs31,
                                               float (&acc)[4]) {
     constexpr uint32_t SV = sizeof(T), SX = sizeof(X);
@@ -314,8 +339,38 @@ __device__ __forceinline__ void tile_half_row(uint32_t a_bm, uint32_t a_xo, uint
             // diagonal block (the +-m neighbours of a stencil, any band at a multiple of 8): row i of the half holds exactly
             // column 4h + i -- four straight multiply-adds, no bit walk (20 instructions instead of ~50)
             const uint32_t xa = xs31 - 31u * SX + (xo + 4u * (uint32_t)h) * SX;
+            float x4[4];
+            if constexpr (XV) lds_x4<X>(xa, x4);
+            else {
 #pragma unroll
-            for (int i = 0; i < 4; i++) acc[i] = fmaf(lds_as_f32<T>(va0 + i * SV), lds_as_f32<X>(xa + i * SX), acc[i]);
+                for (int i = 0; i < 4; i++) x4[i] = lds_as_f32<X>(xa + i * SX);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc[i] = fmaf(lds_as_f32<T>(va0 + i * SV), x4[i], acc[i]);
+        } else if (w == (h ? 0x1C0E0703u : 0xC0E07038u)) {
+            // tridiagonal block (the diagonal block of a stencil, any 3-wide band): row i of the half holds columns
+            // 4h+i-1 .. 4h+i+1, clipped to the block -- 11 values.  Written as 12 slots (3 per row) over the six x elements
+            // 4h-1 .. 4h+4 so that the code does not depend on h: slot 0 of the upper half (column -1) and slot 11 of the
+            // lower half (column 8) do not exist and are predicated off (their loads stay inside the staged tile).
+            const uint32_t vb = va0 + ((uint32_t)h - 1u) * SV;                       // slot s at vb + s * SV
+            const uint32_t xa = xs31 - 31u * SX + (xo + 4u * (uint32_t)h - 1u) * SX;   // x[4h-1+j] at xa + j * SX
+            float xl[6], v[12];
+            if constexpr (XV) {
+                float x4[4];
+                lds_x4<X>(xa + SX, x4);
+                xl[0] = lds_as_f32<X>(xa); xl[1] = x4[0]; xl[2] = x4[1]; xl[3] = x4[2]; xl[4] = x4[3]; xl[5] = lds_as_f32<X>(xa + 5 * SX);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 6; j++) xl[j] = lds_as_f32<X>(xa + j * SX);
+            }
+#pragma unroll
+            for (int s = 0; s < 12; s++) v[s] = lds_as_f32<T>(vb + s * SV);
+            if (h) acc[0] = fmaf(v[0], xl[0], acc[0]);
+            acc[0] = fmaf(v[1], xl[1], acc[0]); acc[0] = fmaf(v[2], xl[2], acc[0]);
+            acc[1] = fmaf(v[3], xl[1], acc[1]); acc[1] = fmaf(v[4], xl[2], acc[1]); acc[1] = fmaf(v[5], xl[3], acc[1]);
+            acc[2] = fmaf(v[6], xl[2], acc[2]); acc[2] = fmaf(v[7], xl[3], acc[2]); acc[2] = fmaf(v[8], xl[4], acc[2]);
+            acc[3] = fmaf(v[9], xl[3], acc[3]); acc[3] = fmaf(v[10], xl[4], acc[3]);
+            if (!h) acc[3] = fmaf(v[11], xl[5], acc[3]);
         } else if (w && !(w & (w - 1u))) {
             // one value in this half (the +-1 neighbours of a stencil: a single cell in the whole block): one product, added to
             // the row it belongs to
@@ -616,6 +671,249 @@ __global__ void __launch_bounds__(RTT * TPR, MINB) spmv_tile_kernel(const TileAr
     }
 }
 
+
+// ===================================================================================== path 0, streaming kernel
+// Persistent CTAs, warp-specialised.  The one-CTA-per-tile kernel above holds a tile's shared memory through three dependent
+// global latencies (descriptor -> line list -> x lines) before it computes anything: with shared memory as the limiting
+// resource that idle time is what caps the bytes in flight (ncu, round 1: 58 % of the stall samples sit in that prologue).
+// Here a CTA is NG groups; a group is one producer warp plus 2*RTT consumer threads (two per block row, one per 32-bit bitmap
+// half) and owns `spg` tile-sized stages of shared memory.  Group g of CTA b takes the tiles b + (g + k NG) gridDim.x, k = 0, 1, ..
+// -- the SMs sweep the matrix together, so the x lines shared by neighbouring tiles are in L2 at the same time.
+//   producer (one elected lane): keeps the 64-byte descriptors of its next tiles arriving by cp.async in a small ring, and as
+//     soon as a stage is released issues the tile's bulk copies -- row pointers, bitmaps, x offsets, values, and the tile's x
+//     lines as one copy per run of consecutive lines (three runs for a 5-point stencil; line by line, all lanes, for scattered
+//     tiles) -- all completing on the stage's `full` mbarrier.  A stage waits for ONE memory latency, not three.
+//   consumers: wait for `full`, multiply out of shared memory, store y, arrive on the stage's `empty` mbarrier.
+// No CTA-wide barrier after start-up.  One producer warp serves one group: a warp issues its ~200 instructions per tile at one
+// every few cycles, so a single producer for a whole CTA of seven groups caps the SM at one tile per 0.7 us (measured).
+struct StageLayout { uint32_t bm, xo, val, row, xs, stride; };
+inline StageLayout stage_layout(int rt, int cap_blk, int cap_val, int cap_lines, int vsize, int xsize) {
+    auto up16 = [](uint32_t v) { return (v + 15u) & ~15u; };
+    StageLayout s;
+    s.bm = 16;                                                   // 16-byte header: {p0, v0, staged, -}
+    s.xo = up16(s.bm + (uint32_t)(cap_blk + 2) * 8);
+    s.val = up16(s.xo + (uint32_t)(cap_blk + 16) * 2);
+    s.row = up16(s.val + (uint32_t)(cap_val + 16) * vsize);
+    s.xs = up16(s.row + (uint32_t)(rt + 2) * 8);
+    s.stride = (s.xs + (uint32_t)cap_lines * 32u * xsize + 16u + 127u) & ~127u;   // + 16: the tridiagonal path reads one element past
+    return s;
+}
+
+template <typename T>
+struct StreamArgs {
+    TileArgs<T> t;
+    StageLayout so;
+    int32_t spg, ntiles;         // stages per group; tiles of this launch (tile0 .. tile0 + ntiles)
+};
+
+__device__ __forceinline__ int4 lds_v4(uint32_t a) {
+    int4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+constexpr int STREAM_DR = 8, STREAM_PD = 4;      // descriptor ring slots / prefetch distance of a producer
+
+template <typename T, typename X, int RTT, int NG, int MINB, typename H = NoHalo>
+__global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(const StreamArgs<T> sa, const X* __restrict__ x, float* __restrict__ y,
+                                                                               const H hd) {
+    constexpr bool DIST = !std::is_same<H, NoHalo>::value;
+    constexpr int GT = RTT * 2;            // consumer threads of a group: two per block row
+    constexpr int VA = 16 / sizeof(T);
+    constexpr uint32_t SX = sizeof(X);
+    constexpr int DR = STREAM_DR, PD = STREAM_PD;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const TileArgs<T>& a = sa.t;
+    const StageLayout so = sa.so;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int spg = sa.spg, nstage = spg * NG;
+    const uint32_t sbase = smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)nstage * so.stride);      // full[nstage], empty[nstage]
+    if (tid == 0) {
+        for (int s = 0; s < nstage; s++) { mbar_init(bars + s, 1); mbar_init(bars + nstage + s, GT / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const bool is_producer = warp < NG;
+    const int g = NG == 1 ? 0 : (is_producer ? warp : (warp - NG) / (GT / 32));
+    const int grid = (int)gridDim.x;
+    // this group's tiles: q_k = blockIdx.x + (g + k NG) * grid, k = 0 .. n_k - 1
+    const int q0 = (int)blockIdx.x + g * grid, qstep = NG * grid;
+    const int n_k = q0 < sa.ntiles ? (sa.ntiles - q0 + qstep - 1) / qstep : 0;
+    // DIST: the tile order is rotated by half the launch so that the boundary tiles (which wait for the peers' rows and produce the
+    // rows the peers wait for) run mid-kernel.
+    auto tile_of = [&](int k) {
+        int q = q0 + k * qstep;
+        if constexpr (DIST) { q += hd.rot; if (q >= sa.ntiles) q -= sa.ntiles; }
+        return a.tile0 + q;
+    };
+    // the group's stages and their barriers
+    const uint32_t gbase = sbase + (uint32_t)(g * spg) * so.stride;
+    uint64_t* full = bars + g * spg;
+    uint64_t* empty = bars + nstage + g * spg;
+
+    if (is_producer) {
+        // ------------------------------------------------------------------------------------------ producer
+        // The descriptors of the next PD tiles travel global -> shared with cp.async (no register is waited on), one commit group
+        // per tile; group k is complete once at most PD newer groups are pending.
+        const uint32_t ring = sbase + (uint32_t)nstage * (so.stride + 16u) + (uint32_t)g * (DR * 64u);
+        if (lane == 0) {
+            auto prefetch = [&](int k) {
+                if (k < n_k) {
+                    const char* src = reinterpret_cast<const char*>(a.desc + tile_of(k));
+                    const uint32_t dst = ring + (uint32_t)(k % DR) * 64u;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) cp_async16(dst + 16u * c, src + 16 * c);
+                }
+                cp_async_commit();
+            };
+            for (int k = 0; k < PD; k++) prefetch(k);
+        }
+        int s = 0; uint32_t round = 0;
+        for (int k = 0; k < n_k; k++) {
+            int4 d0, d1, d2, d3;
+            if (lane == 0) {
+                // refill the ring, then make sure tile k's descriptor has landed
+                {
+                    const int kk = k + PD;
+                    if (kk < n_k) {
+                        const char* src = reinterpret_cast<const char*>(a.desc + tile_of(kk));
+                        const uint32_t dst = ring + (uint32_t)(kk % DR) * 64u;
+#pragma unroll
+                        for (int c = 0; c < 4; c++) cp_async16(dst + 16u * c, src + 16 * c);
+                    }
+                    cp_async_commit();
+                }
+                cp_async_wait<PD>();
+            }
+            __syncwarp();
+            const uint32_t dsl = ring + (uint32_t)(k % DR) * 64u;
+            d0 = lds_v4(dsl); d1 = lds_v4(dsl + 16); d2 = lds_v4(dsl + 32); d3 = lds_v4(dsl + 48);
+            const int t = tile_of(k);
+            const int p0 = d0.x, nb = d0.y, nv = d0.w, nl = d1.x;
+            const uint32_t v0 = (uint32_t)d0.z, v0a = v0 & ~(uint32_t)(VA - 1);
+            const bool staged = (d1.y & 1) && nb <= a.cap_blk && nv <= a.cap_val && nl <= a.cap_lines;
+            const int r0 = t * RTT, nrow = min(RTT, a.nbr - r0);
+            if (round) mbar_wait(empty + s, (round - 1u) & 1u);          // the stage's previous tile has been consumed
+            const uint32_t sp32 = gbase + (uint32_t)s * so.stride;
+            unsigned char* sp = smem + (size_t)(g * spg + s) * so.stride;
+            const uint32_t nrb = (uint32_t)((nrow + 1 + 1) & ~1) * 8;
+            const int p0a = p0 & ~1, p0x = p0 & ~7;
+            uint32_t n8 = 0, n2 = 0, nvb = 0;
+            int nlc = 0;                                                  // x lines that arrive by bulk copy
+            if (staged && nb > 0) {
+                n8 = (uint32_t)((p0 + nb - p0a + 1) & ~1) * 8;
+                n2 = (uint32_t)((p0 + nb - p0x + 7) & ~7) * 2;
+                nvb = ((v0 + (uint32_t)nv - v0a + (uint32_t)(VA - 1)) & ~(uint32_t)(VA - 1)) * (uint32_t)sizeof(T);
+                nlc = (d1.y & 2) ? nl - 1 : nl;                          // a last line that reaches past the last column is loaded by hand
+            }
+            if (staged && nlc < nl) {
+                const uint32_t col = (uint32_t)d1.w * 32u + (uint32_t)lane;          // lmax is the tile's last line
+                sts_x<X>(sp32 + so.xs + ((uint32_t)(nl - 1) * 32u + (uint32_t)lane) * SX, col < (uint32_t)a.cols ? x[col] : X(0.f));
+                __syncwarp();
+            }
+            if constexpr (DIST) {
+                // A tile whose x lines leave this rank's own columns must not read x before the peers' rows are in, and a tile that
+                // pushes rows waits too (back-pressure, see spmv_tile_kernel).  The producer waits on the tile's behalf before it
+                // completes `full`; the rotated tile order puts these tiles mid-kernel, where the wait is over before it starts.
+                const int trow0 = r0 * 8, trow1 = min(a.rows, (r0 + nrow) * 8);
+                bool part = t == hd.solo_tile;
+                for (int i = 0; i < hd.n_push; i++) part |= hd.lo[i] < trow1 && hd.hi[i] > trow0;
+                if (part || (nb > 0 && ((int64_t)d1.z * 32 < hd.own_c0 || ((int64_t)d1.w + 1) * 32 > hd.own_c1))) {
+                    if (lane < hd.n_peer) halo_wait(hd, lane);
+                    __syncwarp();
+                }
+            }
+            const bool by_runs = d2.x > 0;
+            if (lane == 0) {
+                *reinterpret_cast<int4*>(sp) = make_int4(p0, (int)v0, staged ? 1 : 0, 0);
+                mbar_arrive_expect_tx(full + s, n8 + n2 + nvb + nrb + (uint32_t)nlc * 32u * SX);
+                bulk_g2s(sp + so.row, a.rowpair + r0, nrb, full + s);
+                if (n8) bulk_g2s(sp + so.bm, a.bmps + p0a, n8, full + s);
+                if (n2) bulk_g2s(sp + so.xo, a.xoff + p0x, n2, full + s);
+                if (nvb) bulk_g2s(sp + so.val, a.values + v0a, nvb, full + s);
+                if (nlc > 0 && by_runs) {                                 // up to three runs of consecutive lines
+                    unsigned char* xs = sp + so.xs;
+                    const uint32_t rl[3] = {(uint32_t)d2.y, (uint32_t)d2.z, (uint32_t)d2.w}, rc[3] = {(uint32_t)d3.x, (uint32_t)d3.y, (uint32_t)d3.z};
+                    uint32_t first = 0;
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        if (r < d2.x) {
+                            uint32_t cnt = rc[r];
+                            if (first + cnt > (uint32_t)nlc) cnt = (uint32_t)nlc - first;     // the hand-loaded last line
+                            if (cnt) bulk_g2s(xs + (size_t)first * 32u * SX, x + (size_t)rl[r] * 32u, cnt * 32u * SX, full + s);
+                            first += rc[r];
+                        }
+                    }
+                }
+            }
+            if (nlc > 0 && !by_runs) {                                    // scattered lines: one copy per line, all lanes
+                __syncwarp();                                             // after lane 0's expect_tx
+                unsigned char* xs = sp + so.xs;
+                for (int j = lane; j < nlc; j += 32)
+                    bulk_g2s(xs + (size_t)j * 32u * SX, x + (size_t)__ldg(a.lines + p0 + j) * 32u, 32u * SX, full + s);
+            }
+            if (++s == spg) { s = 0; round++; }
+        }
+    } else {
+        // ------------------------------------------------------------------------------------------ consumers
+        const int gt = tid - NG * 32 - g * GT;
+        const int lbr = gt >> 1, h = gt & 1;
+        int s = 0; uint32_t par = 0;
+        for (int k = 0; k < n_k; k++) {
+            const int t = tile_of(k);
+            const int r0 = t * RTT, nrow = min(RTT, a.nbr - r0);
+            mbar_wait(full + s, par);
+            const uint32_t sb = gbase + (uint32_t)s * so.stride;
+            const int4 hdr = lds_v4(sb);
+            const int p0 = hdr.x; const uint32_t v0a = (uint32_t)hdr.y & ~(uint32_t)(VA - 1);
+            const bool staged = hdr.z != 0;
+            const int row = (r0 + lbr) * 8 + h * 4;
+            const bool active = lbr < nrow && row < a.rows;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (active) {
+                const uint2 rp = lds_v2(sb + so.row + 8u * lbr);          // (first block, first value) of this block row
+                const uint32_t pe = lds_u32(sb + so.row + 8u * lbr + 8u);
+                const uint32_t pb = rp.x, kv = rp.y;
+                if (staged) {
+                    const uint32_t rel = pb - (uint32_t)p0;
+                    const uint32_t a_bm = sb + so.bm + ((uint32_t)(p0 & 1) + rel) * 8u, a_xo = sb + so.xo + ((uint32_t)(p0 & 7) + rel) * 2u;
+                    const uint32_t a_v = sb + so.val + (kv - v0a) * (uint32_t)sizeof(T), xs31 = sb + so.xs + 31u * SX;
+                    tile_half_row<T, X, true>(a_bm, a_xo, a_v, (int)(pe - pb), h, xs31, acc);
+                } else {
+                    half_block_row<T, X>(a.bmps, a.bcol, a.values, (int)pb, (int)pe, kv, h, x, acc);
+                }
+                float* yr = y + row;
+                if (row + 4 <= a.rows) *reinterpret_cast<float4*>(yr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) if (row + q < a.rows) yr[q] = acc[q];
+                }
+            }
+            if constexpr (DIST) {
+                const int trow0 = r0 * 8, trow1 = min(a.rows, (r0 + nrow) * 8);
+                bool part = t == hd.solo_tile;
+                for (int i = 0; i < hd.n_push; i++) part |= hd.lo[i] < trow1 && hd.hi[i] > trow0;
+                if (part) {
+                    if (active) halo_store<4>(hd, row, a.rows, acc);
+                    __threadfence_system();
+                    bar_sync_named(1 + g, GT);
+                    if (gt == 0) halo_signal(hd);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+            if (++s == spg) { s = 0; par ^= 1u; }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ path 1
 // work item: x = block row, y = first block, z = end block, w = 1 when the block row is sliced.
 // One warp per item, UNR x 32 blocks per step: every lane issues the metadata loads of its UNR blocks together, the UNR
@@ -760,11 +1058,7 @@ __global__ void work_fill_kernel(const int32_t* __restrict__ brp, int nbr, const
     }
 }
 
-static int spmv_variant() {
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("BMSP_SPMV_VARIANT"); variant = e ? atoi(e) : 0; }
-    return variant;
-}
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 
 // path 0 plan: tile descriptors, x lines and per-block x offsets; shared-memory capacities from the tile maxima
 // when they fit the per-CTA budget, else from the averages (larger tiles are then read from global memory).
@@ -776,6 +1070,13 @@ static int plan_tiles(bmsp_matrix_s* m, cudaStream_t st) {
     while (rt > 16 && row_bytes * rt > 20.0 * 1024) rt >>= 1;
     if (const char* e = getenv("BMSP_SPMV_RT")) { const int v = atoi(e); if (v == 16 || v == 32 || v == 64 || v == 128) rt = v; }   // experiments
     m->tile_rows = rt;
+    // Light rows (64-block-row tiles: stencils, bands) stream through the persistent kernel.  Heavy rows (dense blocks: 16- or
+    // 32-row tiles of 17 KB) are bound by the bit walk, not by memory: a stage then feeds only one or two consumer warps and
+    // the one-CTA-per-tile kernel, which keeps 13 such tiles computing per SM, is faster (BC4M: 280 us vs 479 us).
+    // BMSP_SPMV_KERNEL = 1 / 2 forces the per-tile / the streaming kernel (A/B runs).
+    const int force = env_int("BMSP_SPMV_KERNEL", 0);
+    m->spmv_kernel = force == 1 ? 1 : (force == 2 ? 0 : (rt == 64 ? 0 : 1));
+    m->xl_pitch = m->spmv_kernel == 1 ? XL_STRIDE : 32;
     const int ntiles = (int)ceil_div(m->nbr, rt);
     unsigned long long* stats = nullptr;
     BMSP_TRY(dev_alloc((void**)&m->tile_desc, sizeof(TileDesc) * (size_t)ntiles, st));
@@ -786,7 +1087,7 @@ static int plan_tiles(bmsp_matrix_s* m, cudaStream_t st) {
     BMSP_KERNEL_CHECK();
     BMSP_TRY(dev_alloc_t(&stats, 8, st));
     BMSP_CUDA(cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), st));
-    tile_plan_kernel<<<ntiles, 256, 0, st>>>(m->brp, m->bcol, m->rvb, m->nbr, m->cols, rt, (TileDesc*)m->tile_desc, m->tile_lines, m->tile_xoff, stats);
+    tile_plan_kernel<<<ntiles, 256, 0, st>>>(m->brp, m->bcol, m->rvb, m->nbr, m->cols, rt, m->xl_pitch, (TileDesc*)m->tile_desc, m->tile_lines, m->tile_xoff, stats);
     BMSP_KERNEL_CHECK();
     unsigned long long h[8];
     BMSP_CUDA(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -855,6 +1156,52 @@ static int launch_tile_kernel(const TileArgs<T>& a, const X* x, float* y, const 
     return BMSP_OK;
 }
 
+// Streaming kernel launch.  One group per CTA (NG = 1); MAXB bounds the CTAs per SM the registers allow.  Shared memory decides the
+// rest: as many CTAs per SM as fit with two stages each (a group needs a second stage to have its next tile arriving while it
+// multiplies the current one; P4096: 7 CTAs x 2 stages of 15.4 KB -- the measured optimum).
+template <typename T, typename X, int RTT, int NG, int MAXB, typename H>
+static int launch_stream_kernel(const TileArgs<T>& a, const X* x, float* y, const H& hd, int ntiles, cudaStream_t st) {
+    auto kern = spmv_stream_kernel<T, X, RTT, NG, MAXB, H>;
+    static int sms = 0;
+    static size_t smem_max = 0;
+    if (!sms) {
+        int dev = 0;
+        BMSP_CUDA(cudaGetDevice(&dev));
+        int v = 0;
+        BMSP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        smem_max = (size_t)v;
+        BMSP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    StreamArgs<T> sa;
+    sa.t = a;
+    sa.so = stage_layout(RTT, a.cap_blk, a.cap_val, a.cap_lines, sizeof(T), sizeof(X));
+    sa.ntiles = ntiles;
+    const size_t fixed = (size_t)NG * STREAM_DR * 64 + 64;                               // descriptor rings
+    const size_t per_stage = (size_t)NG * (sa.so.stride + 16);
+    static const int want_ctas = env_int("BMSP_SPMV_CTAS", 0), want_spg = env_int("BMSP_SPMV_STAGES", 0);   // experiments
+    int ctas = 0, spg = 0;
+    size_t per_cta = 0;
+    for (int c = want_ctas > 0 ? std::min(want_ctas, MAXB) : MAXB; c >= 1; c--) {
+        per_cta = std::min<size_t>(smem_max / c - 1024 - 256, 227 * 1024);               // 1 KB per resident CTA is the system's; 256 B allocation granule
+        const int fit = per_cta > fixed ? (int)((per_cta - fixed) / per_stage) : 0;
+        if (fit >= 2 || (c == 1 && fit >= 1)) { ctas = c; spg = std::min(fit, 8); break; }
+    }
+    if (want_spg > 0) spg = std::min(spg, want_spg);
+    if (ctas < 1 || spg < 1) { set_error("spmv: a tile stage of %u bytes does not fit shared memory", sa.so.stride); return BMSP_ERR_CUDA; }
+    sa.spg = spg;
+    const size_t smem = (size_t)spg * per_stage + fixed;
+    static size_t configured = 0;            // per instantiation
+    if (configured < smem || configured == 0) {
+        BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        BMSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured = std::max<size_t>(smem, 1);
+    }
+    const int grid = std::max(1, std::min((int)ceil_div(ntiles, NG), sms * ctas));
+    kern<<<(unsigned)grid, NG * (32 + RTT * 2), smem, st>>>(sa, x, y, hd);
+    BMSP_KERNEL_CHECK();
+    return BMSP_OK;
+}
+
 // tile0 / ntiles: path 0 only -- launch the tiles [tile0, tile0 + ntiles) (ntiles < 0: all of them).
 // hd: NoHalo, or HaloDev for the fused multi-GPU product (path 0, fp32 x, all tiles).
 template <typename T, typename X, typename H = NoHalo>
@@ -870,15 +1217,18 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, 
         const size_t smem = a.so.total;
         const int grid = ntiles < 0 ? (int)ceil_div(A->nbr, rt) : ntiles;
         if (grid <= 0) return BMSP_OK;
+        if (A->spmv_kernel == 0) {
+            // streaming kernel: one group (a producer warp + 2 * rt consumer threads) per CTA; CTAs per SM bounded by registers
+            if (rt == 128) return launch_stream_kernel<T, X, 128, 1, 3, H>(a, x, y, hd, grid, st);
+            if (rt == 32) return launch_stream_kernel<T, X, 32, 1, 8, H>(a, x, y, hd, grid, st);
+            if (rt == 16) return launch_stream_kernel<T, X, 16, 1, 8, H>(a, x, y, hd, grid, st);
+            return launch_stream_kernel<T, X, 64, 1, 7, H>(a, x, y, hd, grid, st);
+        }
         // default: one thread per bitmap half; BMSP_SPMV_VARIANT=1: one thread per block row (64-row tiles only).
         // Measured on P4096: 92.7 us vs 103.5 us (fewer instructions, but too few warps to hide the staging latency).
         if (rt == 128) return launch_tile_kernel<T, X, 128, 2, 6, H>(a, x, y, hd, grid, smem, st);
         if (rt == 32) return launch_tile_kernel<T, X, 32, 2, 24, H>(a, x, y, hd, grid, smem, st);
         if (rt == 16) return launch_tile_kernel<T, X, 16, 2, 32, H>(a, x, y, hd, grid, smem, st);
-        if constexpr (std::is_same<H, NoHalo>::value) {
-            if (spmv_variant() == 1) return launch_tile_kernel<T, X, 64, 1, 14, H>(a, x, y, hd, grid, smem, st);
-            if (spmv_variant() == 3) return launch_tile_kernel<T, X, 64, 2, 14, H>(a, x, y, hd, grid, smem, st);
-        }
         return launch_tile_kernel<T, X, 64, 2, 12, H>(a, x, y, hd, grid, smem, st);
     }
     const unsigned grid1 = (unsigned)ceil_div(A->n_work, 8), grid2 = (unsigned)ceil_div((int64_t)A->n_split_rows * 8, 256);

@@ -177,5 +177,36 @@ def rmat_torch(scale: int, edge_factor: int = 16, a=0.57, b=0.19, c=0.19, seed: 
     return n, n, rp.to(torch.int32), (key & 0xFFFFFFFF).to(torch.int32), values_fp16_torch(seed, key.numel(), device)
 
 
+def block_clustered_torch(nbr: int, half_band: int = 16, p_block: float = 0.30, seed: int = 3, device="cuda"):
+    """block_clustered() above, bit-identical, as torch tensors on `device` (the 4M-row config takes 30 s in numpy)."""
+    import torch
+    W = 2 * half_band
+    I = torch.arange(nbr, dtype=torch.int64, device=device)[:, None]
+    d = torch.arange(W, dtype=torch.int64, device=device)[None, :]
+    J = I + d - half_band
+    lin = I * W + d
+    present = (_unit_torch(seed, lin) < p_block) | (J == I)
+    present &= (J >= 0) & (J < nbr)
+    mask = splitmix64_torch(seed + 101, lin)
+    mask = torch.where(mask == 0, torch.ones_like(mask), mask)
+    mask = torch.where(present, mask, torch.zeros_like(mask))
+    del present, lin, J
+    # byte ri (MSB first) of each mask = row ri of the block; bit (MSB first) = column
+    shifts = (56 - 8 * torch.arange(8, dtype=torch.int64, device=device))[None, :, None]         # [1, ri, 1]
+    rows_bytes = (_t_lsr(mask[:, None, :], 0) >> shifts) & 0xFF                                      # [I, ri, d]
+    del mask
+    bitpos = (7 - torch.arange(8, dtype=torch.int64, device=device))[None, None, None, :]
+    bits = ((rows_bytes[..., None] >> bitpos) & 1).to(torch.bool).reshape(nbr * 8, W * 8)           # [I*8 + ri, d*8 + ci]
+    del rows_bytes
+    n = nbr * 8
+    rp = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    rp[1:] = torch.cumsum(bits.sum(dim=1), 0)
+    nz = torch.nonzero(bits)                                                                         # row-major, like np.flatnonzero
+    del bits
+    rowi, within = nz[:, 0], nz[:, 1]
+    col = (rowi // 8 - half_band) * 8 + within
+    return n, n, rp.to(torch.int32), col.to(torch.int32), values_fp16_torch(seed, int(col.numel()), device)
+
+
 def x_vector(n: int, seed: int = 1) -> np.ndarray:
     return (_unit(seed ^ 0xABCD, np.arange(n, dtype=np.uint64)) * 2.0 - 1.0).astype(np.float32)

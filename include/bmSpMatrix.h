@@ -19,6 +19,16 @@
 #include <vector>
 #include "bmsparse_b200.h"
 
+/* Translation units that are compiled by nvcc and can see Thrust also get the reference's Thrust-typed signatures (the adopting
+ * constructor of include/bmSpMatrix.h:33-34 and the five-argument mmread_bmSparse of include/reader.h:14-15), so that reference
+ * call sites compile unchanged.  Define BMSP_NO_THRUST to keep Thrust out. */
+#if !defined(BMSP_NO_THRUST) && defined(__CUDACC__) && defined(__has_include)
+#if __has_include(<thrust/device_vector.h>)
+#include <thrust/device_vector.h>
+#define BMSP_HAVE_THRUST 1
+#endif
+#endif
+
 #define BLOCK_WIDTH 8
 #define BLOCK_HEIGHT 8
 #define BMSP_BLOCK_SIZE (BLOCK_WIDTH * BLOCK_HEIGHT)
@@ -65,6 +75,21 @@ public:
                                             bmsp::dtype_of<valueType>::value, BMSP_DEVICE, transposed ? 1 : 0, stream, &h_));
         refresh();
     }
+#ifdef BMSP_HAVE_THRUST
+    /* the reference's own signature (include/bmSpMatrix.h:33-34): adopts the four vectors.  The reference swaps them into the
+     * object (src/bmSpMatrix.cu:38-42), leaving the caller's vectors empty; here the arrays are copied into the handle and the
+     * caller's vectors are released, which is the same observable state. */
+    bmSpMatrix(int rows, int cols, int blocks, thrust::device_vector<uint64_t>& k, thrust::device_vector<uint64_t>& b,
+               thrust::device_vector<uint64_t>& o, thrust::device_vector<valueType>& v) : h_(nullptr) {
+        bmsp::check(bmsp_create_from_arrays(rows, cols, blocks, (int64_t)v.size(), thrust::raw_pointer_cast(k.data()),
+                                            thrust::raw_pointer_cast(b.data()), thrust::raw_pointer_cast(o.data()), (int64_t)o.size(),
+                                            thrust::raw_pointer_cast(v.data()), bmsp::dtype_of<valueType>::value, BMSP_DEVICE, 0, nullptr, &h_));
+        cudaStreamSynchronize(0);
+        thrust::device_vector<uint64_t>().swap(k); thrust::device_vector<uint64_t>().swap(b); thrust::device_vector<uint64_t>().swap(o);
+        thrust::device_vector<valueType>().swap(v);
+        refresh();
+    }
+#endif
     /* the CSR entry point the north star adds (CSRMatrix.h role): host or device CSR */
     static bmSpMatrix from_csr(int rows, int cols, int64_t n, const int32_t* row_ptr, const int32_t* col_idx, const float* vals,
                                bool on_device, bool transpose, void* stream = nullptr) {

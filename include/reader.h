@@ -29,4 +29,22 @@ inline std::tuple<int, int, int> mmread_bmSparse(const std::string& path, bmSpMa
     out.adopt(h);
     return std::make_tuple(nr, nc, nl);
 }
+
+#ifdef BMSP_HAVE_THRUST
+#include <thrust/tuple.h>
+#include <cuda_fp16.h>
+/* The reference's signature, include/reader.h:14-15 (defined in src/reader.cu:49-110): fills the caller's four device vectors. */
+typedef thrust::device_vector<uint64_t> uint64_vec;
+typedef thrust::device_vector<__half> half_vec;
+inline thrust::tuple<int, int, int> mmread_bmSparse(std::string path, uint64_vec& keys, uint64_vec& bmps, uint64_vec& offsets, half_vec& values) {
+    bmSpMatrix<bmsp::half_t> m;
+    const std::tuple<int, int, int> dims = mmread_bmSparse(path, m);
+    keys.resize(m.keys.size()); bmps.resize(m.bmps.size()); offsets.resize(m.offsets.size()); values.resize(m.values.size());
+    cudaMemcpy(thrust::raw_pointer_cast(keys.data()), m.keys.data(), 8 * m.keys.size(), cudaMemcpyDeviceToDevice);
+    cudaMemcpy(thrust::raw_pointer_cast(bmps.data()), m.bmps.data(), 8 * m.bmps.size(), cudaMemcpyDeviceToDevice);
+    cudaMemcpy(thrust::raw_pointer_cast(offsets.data()), m.offsets.data(), 8 * m.offsets.size(), cudaMemcpyDeviceToDevice);
+    cudaMemcpy(thrust::raw_pointer_cast(values.data()), m.values.data(), 2 * m.values.size(), cudaMemcpyDeviceToDevice);
+    return thrust::make_tuple(std::get<0>(dims), std::get<1>(dims), std::get<2>(dims));
+}
+#endif
 #endif /* READER_HPP_ */

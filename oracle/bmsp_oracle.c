@@ -392,3 +392,181 @@ int orc_max_threads(void) {
     return 1;
 #endif
 }
+
+/* Launchers such as torch.distributed.run export OMP_NUM_THREADS=1 to their workers; the CPU baseline must still use the
+ * box's cores.  Sets the OpenMP thread count of the calling thread's subsequent parallel regions (the reference's cusp OMP
+ * kernels in oracle/_ref share this OpenMP runtime) and returns the value now in effect. */
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
+/* ================================================================ OpenMP variants for full-size parity (test infrastructure)
+ * Same definitions as orc_coo_to_bmsp / orc_spgemm above (which follow the reference line by line and are pinned to its golden
+ * vectors), evaluated one block row at a time so that the BASELINE.json sizes finish in seconds on the GPU box's host cores.
+ * tests/test_oracle_golden.py checks them bit for bit against the scalar functions. */
+
+/* CSR (columns ascending in each row) -> bmSparse.  A block row is the 8-way merge of its rows: blocks in ascending block
+ * column (src/bmSpMatrix.cu:45-74, block_order), cells of a block in row-major (plain) or column-major (transposed operand)
+ * order (:85-101).  Two-call protocol: keys == NULL returns the block count; then fill (keys/bmps/offsets: nblk, values: nnz). */
+int64_t orc_csr_to_bmsp_omp(int rows, const int32_t *rp, const int32_t *ci, const float *vals, int transposed,
+                            uint64_t *keys, uint64_t *bmps, uint64_t *offsets, float *values_out) {
+    const int nbr = (rows + 7) / 8;
+    int64_t *cnt = (int64_t *)calloc((size_t)nbr + 1, sizeof(int64_t));
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int br = 0; br < nbr; br++) {
+        int64_t p[8], e[8];
+        for (int q = 0; q < 8; q++) { int r = br * 8 + q; p[q] = r < rows ? rp[r] : 0; e[q] = r < rows ? rp[r + 1] : 0; }
+        int64_t n = 0;
+        for (;;) {
+            int64_t bc = -1;
+            for (int q = 0; q < 8; q++) if (p[q] < e[q]) { int64_t c = ci[p[q]] >> 3; if (bc < 0 || c < bc) bc = c; }
+            if (bc < 0) break;
+            for (int q = 0; q < 8; q++) while (p[q] < e[q] && (ci[p[q]] >> 3) == bc) p[q]++;
+            n++;
+        }
+        cnt[br + 1] = n;
+    }
+    for (int br = 0; br < nbr; br++) cnt[br + 1] += cnt[br];
+    const int64_t nblk = cnt[nbr];
+    if (!keys) { free(cnt); return nblk; }
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int br = 0; br < nbr; br++) {
+        int64_t p[8], e[8];
+        for (int q = 0; q < 8; q++) { int r = br * 8 + q; p[q] = r < rows ? rp[r] : 0; e[q] = r < rows ? rp[r + 1] : 0; }
+        int64_t b = cnt[br];
+        int64_t w = br * 8 < rows ? rp[br * 8] : 0;         /* values of a block row are contiguous: they start at its first row */
+        for (;;) {
+            int64_t bc = -1;
+            for (int q = 0; q < 8; q++) if (p[q] < e[q]) { int64_t c = ci[p[q]] >> 3; if (bc < 0 || c < bc) bc = c; }
+            if (bc < 0) break;
+            uint64_t bmp = 0;
+            int64_t s[8], t[8];
+            for (int q = 0; q < 8; q++) { s[q] = p[q]; while (p[q] < e[q] && (ci[p[q]] >> 3) == bc) p[q]++; t[q] = p[q]; }
+            keys[b] = ((uint64_t)(uint32_t)br << 32) | (uint64_t)(uint32_t)bc; offsets[b] = (uint64_t)w;
+            if (!transposed) {
+                for (int q = 0; q < 8; q++) for (int64_t i = s[q]; i < t[q]; i++) { bmp |= (uint64_t)1 << (63 - (q * 8 + (ci[i] & 7))); values_out[w++] = vals[i]; }
+            } else {
+                for (int c = 0; c < 8; c++) for (int q = 0; q < 8; q++) {
+                    /* at most one entry of row q has column bc*8+c */
+                    for (int64_t i = s[q]; i < t[q]; i++) if ((ci[i] & 7) == c) { bmp |= (uint64_t)1 << (63 - (c * 8 + q)); values_out[w++] = vals[i]; }
+                }
+            }
+            bmps[b] = bmp;
+            b++;
+        }
+    }
+    free(cnt);
+    return nblk;
+}
+
+typedef struct { uint64_t key; int32_t a, b; } rtask_t;
+static int cmp_rtask(const void *x, const void *y) {
+    const rtask_t *p = x, *q = y;
+    if (p->key != q->key) return p->key < q->key ? -1 : 1;
+    if (p->a != q->a) return p->a < q->a ? -1 : 1;
+    return 0;
+}
+
+/* C = A * B^t-operand, one A block row per task (the C blocks of different block rows are independent).  Same candidate rule,
+ * filter, key, bitmap and per-cell sum as orc_spgemm; the pairs of a C block are summed in ascending A-block order in double and
+ * stored as fp32.  a_brp: block-row pointers of A, nbr + 1 entries (derived from a_keys by the caller).
+ * Two-call protocol: C_keys == NULL fills row_blk / row_nnz (nbr + 1 entries each, exclusive prefix sums, [nbr] = totals). */
+int orc_spgemm_omp(int32_t nbr, const int64_t *a_brp, const uint64_t *a_keys, const uint64_t *a_bmps, const uint64_t *a_off,
+                   const float *a_val, int64_t b_nblk, const uint64_t *b_keys, const uint64_t *b_bmps, const uint64_t *b_off,
+                   const float *b_val, int64_t *row_blk, int64_t *row_nnz, uint64_t *C_keys, uint64_t *C_bmps, uint64_t *C_off,
+                   float *C_val) {
+    const int fill = C_keys != NULL;
+    int failed = 0;
+#pragma omp parallel
+    {
+        rtask_t *t = NULL;
+        int64_t cap = 0;
+#pragma omp for schedule(dynamic, 16)
+        for (int32_t br = 0; br < nbr; br++) {
+            int64_t n = 0;
+            for (int64_t a = a_brp[br]; a < a_brp[br + 1]; a++) {
+                const uint64_t k = a_keys[a] & 0xFFFFFFFFu;
+                const int64_t lo = lower_bound_u64(b_keys, b_nblk, k << 32), hi = lower_bound_u64(b_keys, b_nblk, (k + 1) << 32);
+                if (n + (hi - lo) > cap) {
+                    cap = (n + (hi - lo)) * 2 + 64;
+                    t = (rtask_t *)realloc(t, sizeof(rtask_t) * (size_t)cap);
+                    if (!t) { failed = 1; cap = 0; n = 0; break; }
+                }
+                for (int64_t b = lo; b < hi; b++)
+                    if (orc_pair_bitmap(a_bmps[a], b_bmps[b])) {
+                        t[n].key = (a_keys[a] & 0xFFFFFFFF00000000ull) | (b_keys[b] & 0xFFFFFFFFull);
+                        t[n].a = (int32_t)a; t[n].b = (int32_t)b; n++;
+                    }
+            }
+            qsort(t, (size_t)n, sizeof(rtask_t), cmp_rtask);
+            int64_t nb = 0, nnz = 0;
+            const int64_t b0 = fill ? row_blk[br] : 0, v0 = fill ? row_nnz[br] : 0;
+            for (int64_t i = 0; i < n;) {
+                int64_t j = i; uint64_t bmp = 0;
+                while (j < n && t[j].key == t[i].key) { bmp |= orc_pair_bitmap(a_bmps[t[j].a], b_bmps[t[j].b]); j++; }
+                if (fill) {
+                    C_keys[b0 + nb] = t[i].key; C_bmps[b0 + nb] = bmp; C_off[b0 + nb] = (uint64_t)(v0 + nnz);
+                    double acc[64];
+                    for (int p = 0; p < 64; p++) acc[p] = 0.0;
+                    for (int64_t q = i; q < j; q++) {
+                        const uint64_t ab = a_bmps[t[q].a], bb = b_bmps[t[q].b];
+                        const float *av = a_val + a_off[t[q].a], *bv = b_val + b_off[t[q].b];
+                        uint64_t rem = ab;
+                        int ka = 0;
+                        while (rem) {                                  /* A cells in bitmap order: value index ka */
+                            const int pa = __builtin_clzll(rem);
+                            rem &= ~(0x8000000000000000ull >> pa);
+                            const int r = pa >> 3, k = pa & 7;
+                            const double aval = (double)av[ka++];
+                            for (int c = 0; c < 8; c++) {
+                                const int pb = c * 8 + k;               /* B^t: pos = col*8 + row, bmSpMatrix.cu:91-95 */
+                                if ((bb >> (63 - pb)) & 1) acc[r * 8 + c] += aval * (double)bv[cell_rank(bb, pb)];
+                            }
+                        }
+                    }
+                    int64_t w = v0 + nnz;
+                    for (int p = 0; p < 64; p++) if ((bmp >> (63 - p)) & 1) C_val[w++] = (float)acc[p];
+                }
+                nnz += __builtin_popcountll(bmp);
+                nb++;
+                i = j;
+            }
+            if (!fill) { row_blk[br + 1] = nb; row_nnz[br + 1] = nnz; }
+        }
+        free(t);
+    }
+    if (failed) return 1;
+    if (!fill) {
+        row_blk[0] = 0; row_nnz[0] = 0;
+        for (int32_t br = 0; br < nbr; br++) { row_blk[br + 1] += row_blk[br]; row_nnz[br + 1] += row_nnz[br]; }
+    } else {
+        C_off[row_blk[nbr]] = (uint64_t)row_nnz[nbr];
+    }
+    return 0;
+}
+
+/* y = A x, block rows in parallel (same per-row arithmetic as orc_spmv: double products summed in block / bit order) */
+void orc_spmv_omp(int num_rows, int32_t nbr, const int64_t *brp, const uint64_t *keys, const uint64_t *bmps, const uint64_t *offsets,
+                  const float *values, const float *x, double *y) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int32_t br = 0; br < nbr; br++) {
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int64_t b = brp[br]; b < brp[br + 1]; b++) {
+            const int64_t bc = (int64_t)(keys[b] & 0xFFFFFFFFu);
+            uint64_t rem = bmps[b];
+            int64_t k = (int64_t)offsets[b];
+            while (rem) {
+                const int p = __builtin_clzll(rem);
+                rem &= ~(0x8000000000000000ull >> p);
+                acc[p >> 3] += (double)values[k++] * (double)x[bc * 8 + (p & 7)];
+            }
+        }
+        for (int q = 0; q < 8; q++) if ((int64_t)br * 8 + q < num_rows) y[(int64_t)br * 8 + q] = acc[q];
+    }
+}

@@ -163,6 +163,57 @@ def spgemm(a: OracleMatrix, bt: OracleMatrix) -> OracleMatrix:
                         cv[:nnz.value].copy(), False)
 
 
+# ------------------------------------------------------------------ OpenMP variants (full-size parity; pinned to the scalar functions in tests)
+def _brp(keys: np.ndarray, nbr: int) -> np.ndarray:
+    return np.searchsorted(np.ascontiguousarray(keys) >> np.uint64(32), np.arange(nbr + 1, dtype=np.uint64), side="left").astype(np.int64)
+
+
+def csr_to_bmsp_omp(num_rows, num_cols, rp, ci, vals, transposed=False, f16=True) -> OracleMatrix:
+    rp = np.ascontiguousarray(rp, np.int32); ci = np.ascontiguousarray(ci, np.int32)
+    vals = np.ascontiguousarray(vals, np.float32)
+    if f16:
+        vals = f16_round(vals)
+    L = lib(); L.orc_csr_to_bmsp_omp.restype = _i64
+    head = [C.c_int(num_rows), _ptr(rp), _ptr(ci), _ptr(vals), C.c_int(int(transposed))]
+    nb = L.orc_csr_to_bmsp_omp(*head, None, None, None, None)
+    keys = np.empty(max(nb, 1), np.uint64); bmps = np.empty(max(nb, 1), np.uint64); offs = np.empty(max(nb, 1), np.uint64)
+    vout = np.empty(max(ci.size, 1), np.float32)
+    L.orc_csr_to_bmsp_omp(*head, _ptr(keys), _ptr(bmps), _ptr(offs), _ptr(vout))
+    return OracleMatrix(num_rows, num_cols, keys[:nb], bmps[:nb], offs[:nb], vout[:ci.size], transposed)
+
+
+def spmv_omp(m: OracleMatrix, x: np.ndarray) -> np.ndarray:
+    assert not m.transposed
+    nbr = (m.num_rows + 7) // 8
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.zeros(m.num_rows, np.float64)
+    k = np.ascontiguousarray(m.keys); b = np.ascontiguousarray(m.bmps); o = np.ascontiguousarray(m.offsets)
+    v = np.ascontiguousarray(m.values, dtype=np.float32); brp = _brp(k, nbr)
+    lib().orc_spmv_omp(C.c_int(m.num_rows), C.c_int(nbr), _ptr(brp), _ptr(k), _ptr(b), _ptr(o), _ptr(v), _ptr(x), _ptr(y))
+    return y
+
+
+def spgemm_omp(a: OracleMatrix, bt: OracleMatrix) -> OracleMatrix:
+    """orc_spgemm, one A block row per OpenMP task; values fp32 (rounded from the double sums)."""
+    assert not a.transposed and bt.transposed
+    nbr = (a.num_rows + 7) // 8
+    ak, ab, ao = (np.ascontiguousarray(t) for t in (a.keys, a.bmps, a.offsets))
+    av = np.ascontiguousarray(a.values, dtype=np.float32)
+    bk, bb, bo = (np.ascontiguousarray(t) for t in (bt.keys, bt.bmps, bt.offsets))
+    bv = np.ascontiguousarray(bt.values, dtype=np.float32)
+    brp = _brp(ak, nbr)
+    rb = np.zeros(nbr + 1, np.int64); rn = np.zeros(nbr + 1, np.int64)
+    head = [C.c_int(nbr), _ptr(brp), _ptr(ak), _ptr(ab), _ptr(ao), _ptr(av), _i64(bt.block_num), _ptr(bk), _ptr(bb), _ptr(bo), _ptr(bv),
+            _ptr(rb), _ptr(rn)]
+    if lib().orc_spgemm_omp(*head, None, None, None, None):
+        raise MemoryError("orc_spgemm_omp")
+    nb, nnz = int(rb[nbr]), int(rn[nbr])
+    ck = np.empty(max(nb, 1), np.uint64); cb = np.empty(max(nb, 1), np.uint64); co = np.empty(nb + 1, np.uint64); cv = np.empty(max(nnz, 1), np.float32)
+    if lib().orc_spgemm_omp(*head, _ptr(ck), _ptr(cb), _ptr(co), _ptr(cv)):
+        raise MemoryError("orc_spgemm_omp")
+    return OracleMatrix(a.num_rows, bt.num_cols, ck[:nb], cb[:nb], co, cv[:nnz], False)
+
+
 # ------------------------------------------------------------------ cusp host CSR kernels
 def csr_spmv(rp, ci, v, x, threads=1) -> np.ndarray:
     rp = np.ascontiguousarray(rp, np.int32); ci = np.ascontiguousarray(ci, np.int32)
@@ -222,6 +273,17 @@ def poisson5pt(m: int, n: int):
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+def use_all_cores() -> int:
+    """Undo an inherited OMP_NUM_THREADS=1 (torch.distributed.run exports it to every worker): the CPU baselines run on every
+    core the process may use.  Returns the OpenMP thread count now in effect."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_threads.restype = C.c_int
+    return int(lib().orc_set_threads(C.c_int(n)))
 
 
 def read_mtx(path):
@@ -284,6 +346,50 @@ def run_ref_spgemm(a: OracleMatrix, bt: OracleMatrix, workdir, tc_version=5, mod
         for p in (pa, pb, pc):
             os.remove(p)
     return OracleMatrix(int(h[0]), int(h[1]), k, b, o, v, False), us
+
+
+def sha256_u64(arr) -> str:
+    """SHA-256 of the little-endian bytes of a uint64 array (what oracle/ref_bmsparse_driver.cu prints for the reference's arrays)."""
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(arr, dtype="<u8").tobytes() if arr.size < (1 << 24) else memoryview(np.ascontiguousarray(arr, dtype="<u8"))).hexdigest()
+
+
+def run_ref_spgemm_digest(a: OracleMatrix, bt: OracleMatrix, workdir, tc_version=5, mode=0, reps=1, sample_blocks=0, reuse_inputs=False):
+    """Run the reference's bmSparse_mult<half,float> without dumping C (sample_blocks = 0) or dumping three windows of
+    `sample_blocks` C blocks (first / middle / last).  Returns a dict: us, c_blocks, c_nnz, sha256 {keys, bmps, offsets},
+    offsets_len, and `windows`: [{first_block, keys, bmps, offsets, first_value, values}] when sampled."""
+    exe = ref_cuda_bin("ref_spgemm")
+    pa, pb, pc = (os.path.join(workdir, n) for n in ("refA.bin", "refB.bin", "refCs.bin"))
+    if not (reuse_inputs and os.path.exists(pa) and os.path.exists(pb)):
+        write_bin(pa, a, np.float16); write_bin(pb, bt, np.float16)
+    out_path = pc if sample_blocks > 0 else "-"
+    out = subprocess.run([exe, pa, pb, out_path, str(tc_version), str(mode), str(reps), str(int(sample_blocks))], capture_output=True, text=True, timeout=1800)
+    line = [l for l in out.stdout.splitlines() if l.startswith("REF_SPGEMM_US")]
+    sha = [l for l in out.stdout.splitlines() if l.startswith("REF_SPGEMM_SHA256")]
+    if out.returncode != 0 or not line or not sha:
+        raise RuntimeError(f"reference spgemm failed: rc={out.returncode}\n{out.stdout[-2000:]}\n{out.stderr[-2000:]}")
+    tok = line[0].split()
+    if int(tok[7]) != 0:
+        raise RuntimeError(f"reference spgemm left CUDA error {tok[7]}")
+    st = sha[0].split()
+    res = {"us": float(tok[1]), "c_blocks": int(tok[3]), "c_nnz": int(tok[5]),
+           "sha256": {"keys": st[2], "bmps": st[4], "offsets": st[6]}, "offsets_len": int(st[8]), "windows": []}
+    if sample_blocks > 0:
+        with open(pc, "rb") as f:
+            h = np.fromfile(f, np.int64, 5)
+            if h[2] >= 0:       # small product: the driver dumped everything
+                nb = int(h[2])
+                k = np.fromfile(f, np.uint64, nb); b = np.fromfile(f, np.uint64, nb); o = np.fromfile(f, np.uint64, int(h[4])); v = np.fromfile(f, np.float32, int(h[3]))
+                res["windows"].append({"first_block": 0, "keys": k, "bmps": b, "offsets": o, "first_value": 0, "values": v})
+            else:
+                for _ in range(int(h[4])):
+                    wh = np.fromfile(f, np.int64, 4)
+                    n = int(wh[1])
+                    k = np.fromfile(f, np.uint64, n); b = np.fromfile(f, np.uint64, n); o = np.fromfile(f, np.uint64, n + 1)
+                    v = np.fromfile(f, np.float32, int(wh[3]))
+                    res["windows"].append({"first_block": int(wh[0]), "keys": k, "bmps": b, "offsets": o, "first_value": int(wh[2]), "values": v})
+        os.remove(pc)
+    return res
 
 
 def run_ref_spmv(a: OracleMatrix, workdir, reps=1):

@@ -156,3 +156,43 @@ def test_oracle_matches_recorded_reference_cuda_outputs(oracle):
         assert abs(float(exp.values.sum()) - r["values_sum"]) <= 2e-3 * float(np.abs(exp.values).sum()) + 1e-6, name
     y = O.spmv(a32, np.ones(4096, np.float32))
     assert float(y.sum()) == rec["poisson64_spmv_ones"]["y_sum"] and float(np.abs(y).sum()) == rec["poisson64_spmv_ones"]["y_abs_sum"]
+
+
+def test_openmp_variants_match_the_scalar_oracle(oracle):
+    """oracle/bmsp_oracle.c's block-row-parallel conversion / SpMV / SpGEMM (used for the full-size GPU parity tests) are the same
+    functions as the scalar, reference-following ones: bit for bit on random matrices with empty block rows and on the fixture."""
+    O = oracle
+    from tests.util import random_csr
+    cases = [(24, 24, 0.3, 1, ()), (61, 29, 0.2, 2, ()), (513, 300, 0.05, 3, (0, 2)), (1000, 1000, 0.01, 4, (3,)), (200, 2049, 0.3, 5, ())]
+    for nr, nc, den, seed, emp in cases:
+        rp, ci, v = random_csr(nr, nc, den, seed, emp)
+        for tr in (False, True):
+            a = O.csr_to_bmsp(nr, nc, rp, ci, v, transposed=tr); b = O.csr_to_bmsp_omp(nr, nc, rp, ci, v, transposed=tr)
+            assert np.array_equal(a.keys, b.keys) and np.array_equal(a.bmps, b.bmps) and np.array_equal(a.offsets, b.offsets)
+            assert np.array_equal(a.values, b.values)
+        rp2, ci2, v2 = random_csr(nc, nr, den, seed + 10)
+        A = O.csr_to_bmsp(nr, nc, rp, ci, v); Bt = O.csr_to_bmsp(nc, nr, rp2, ci2, v2, transposed=True)
+        c1 = O.spgemm(A, Bt); c2 = O.spgemm_omp(A, Bt)
+        assert np.array_equal(c1.keys, c2.keys) and np.array_equal(c1.bmps, c2.bmps) and np.array_equal(c1.offsets, c2.offsets)
+        assert np.array_equal(c1.values.astype(np.float32), c2.values)
+        x = np.random.default_rng(0).uniform(-1, 1, nc).astype(np.float32)
+        assert np.array_equal(O.spmv(A, x), O.spmv_omp(A, x))
+    g = load_golden("ragusa16.json")
+    A = O.coo_to_bmsp(24, 24, g["A"]["rows"], g["A"]["cols"], g["A"]["vals"])
+    Bt = O.coo_to_bmsp(24, 24, g["B"]["rows"], g["B"]["cols"], g["B"]["vals"], transposed=True)
+    c = O.spgemm_omp(A, Bt)
+    assert c.nnz == 255 and c.block_num == 9
+
+
+def test_sha256_of_structure_arrays(oracle):
+    import hashlib
+    a = np.arange(1000, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    assert oracle.sha256_u64(a) == hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def test_block_clustered_torch_is_bit_identical():
+    import torch
+    from bmsparse_spgemm_spmv_b200 import generators as G
+    for nbr in (40, 300):
+        a = G.block_clustered(nbr); b = G.block_clustered_torch(nbr, device="cpu")
+        assert a[0] == b[0] and np.array_equal(a[2], b[2].numpy()) and np.array_equal(a[3], b[3].numpy()) and np.array_equal(a[4], b[4].numpy())

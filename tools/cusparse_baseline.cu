@@ -2,7 +2,7 @@
 // Plays the role of the reference's src/cuSparse_spmv.cu (generic-API CSR SpMV, ALG1, fp32) and of
 // src/cuSparse_mult.cu (whose csrgemm2 was removed in CUDA 12: rebuilt on cusparseSpGEMM_*).  Own code.
 //   cusparse_baseline spmv   <csr.bin> [reps]
-//   cusparse_baseline spgemm <csr.bin> [reps]      (C = A*A)
+//   cusparse_baseline spgemm <csr.bin> [reps] [alg]      (C = A*A; alg 0 = first of ALG1, ALG3, ALG2 that fits)
 // csr.bin: int64 rows, cols, nnz; int32 row_ptr[rows+1]; int32 col_idx[nnz]; float vals[nnz]
 #include <cuda_runtime.h>
 #include <cusparse.h>
@@ -57,34 +57,70 @@ int main(int argc, char** argv) {
         printf("CUSPARSE_SPMV_MS %.4f rows %lld nnz %lld ysum %.6g\n", best, rows, nnz, s);
         return 0;
     }
+    // SpGEMM: ALG1 (the default, fastest, memory-hungry) first; when it reports insufficient resources fall back to ALG3 / ALG2,
+    // the memory-bounded variants (estimateMemory with a chunk fraction), so that every BASELINE config gets a cuSPARSE number.
     float best = 1e30f; long long c_nnz = 0;
-    for (int r = 0; r < reps + 1; r++) {
-        cusparseSpMatDescr_t B = A, C;
-        int* c_rp; CK(cudaMalloc(&c_rp, 4 * (rows + 1)));
-        CS(cusparseCreateCsr(&C, rows, cols, 0, c_rp, nullptr, nullptr, CUSPARSE_INDEX_32I, CUSPARSE_INDEX_32I, CUSPARSE_INDEX_BASE_ZERO, CUDA_R_32F));
-        cusparseSpGEMMDescr_t d; CS(cusparseSpGEMM_createDescr(&d));
-        size_t b1 = 0, b2 = 0; void *buf1 = nullptr, *buf2 = nullptr;
-        cudaDeviceSynchronize();
-        cudaEventRecord(e0);
-        const cusparseOperation_t N = CUSPARSE_OPERATION_NON_TRANSPOSE;
-        CS(cusparseSpGEMM_workEstimation(hnd, N, N, &alpha, A, B, &beta, C, CUDA_R_32F, CUSPARSE_SPGEMM_DEFAULT, d, &b1, nullptr));
-        CK(cudaMalloc(&buf1, b1 + 16));
-        CS(cusparseSpGEMM_workEstimation(hnd, N, N, &alpha, A, B, &beta, C, CUDA_R_32F, CUSPARSE_SPGEMM_DEFAULT, d, &b1, buf1));
-        CS(cusparseSpGEMM_compute(hnd, N, N, &alpha, A, B, &beta, C, CUDA_R_32F, CUSPARSE_SPGEMM_DEFAULT, d, &b2, nullptr));
-        CK(cudaMalloc(&buf2, b2 + 16));
-        CS(cusparseSpGEMM_compute(hnd, N, N, &alpha, A, B, &beta, C, CUDA_R_32F, CUSPARSE_SPGEMM_DEFAULT, d, &b2, buf2));
-        int64_t cr, cc, cn; CS(cusparseSpMatGetSize(C, &cr, &cc, &cn));
-        int* c_ci; float* c_v; CK(cudaMalloc(&c_ci, 4 * cn + 16)); CK(cudaMalloc(&c_v, 4 * cn + 16));
-        CS(cusparseCsrSetPointers(C, c_rp, c_ci, c_v));
-        CS(cusparseSpGEMM_copy(hnd, N, N, &alpha, A, B, &beta, C, CUDA_R_32F, CUSPARSE_SPGEMM_DEFAULT, d));
-        cudaEventRecord(e1); cudaEventSynchronize(e1);
-        float ms; cudaEventElapsedTime(&ms, e0, e1);
-        if (r >= 1 && ms < best) best = ms;
-        c_nnz = cn;
-        if (r == 0) printf("cusparse spgemm buffers: %.1f MB + %.1f MB\n", b1 / 1e6, b2 / 1e6);
-        cusparseSpGEMM_destroyDescr(d); cusparseDestroySpMat(C);
-        cudaFree(buf1); cudaFree(buf2); cudaFree(c_rp); cudaFree(c_ci); cudaFree(c_v);
+    const int want_alg = argc > 4 ? atoi(argv[4]) : 0;
+    const cusparseSpGEMMAlg_t algs[3] = {CUSPARSE_SPGEMM_ALG1, CUSPARSE_SPGEMM_ALG3, CUSPARSE_SPGEMM_ALG2};
+    const int alg_id[3] = {1, 3, 2};
+    int used = 0;
+    const cusparseOperation_t N = CUSPARSE_OPERATION_NON_TRANSPOSE;
+    auto once = [&](cusparseSpGEMMAlg_t alg, float* ms_out, long long* nnz_out, bool verbose) -> int {
+        cusparseSpMatDescr_t B = A, C = nullptr;
+        int* c_rp = nullptr; int* c_ci = nullptr; float* c_v = nullptr;
+        void *buf1 = nullptr, *buf2 = nullptr, *buf3 = nullptr;
+        cusparseSpGEMMDescr_t d = nullptr;
+        int rc = 1;
+        size_t b1 = 0, b2 = 0, b3 = 0;
+        do {
+            if (cudaMalloc(&c_rp, 4 * (rows + 1)) != cudaSuccess) break;
+            if (cusparseCreateCsr(&C, rows, cols, 0, c_rp, nullptr, nullptr, CUSPARSE_INDEX_32I, CUSPARSE_INDEX_32I, CUSPARSE_INDEX_BASE_ZERO, CUDA_R_32F)) break;
+            if (cusparseSpGEMM_createDescr(&d)) break;
+            cudaDeviceSynchronize();
+            cudaEventRecord(e0);
+            if (cusparseSpGEMM_workEstimation(hnd, N, N, &alpha, A, B, &beta, C, CUDA_R_32F, alg, d, &b1, nullptr)) break;
+            if (cudaMalloc(&buf1, b1 + 16) != cudaSuccess) break;
+            if (cusparseSpGEMM_workEstimation(hnd, N, N, &alpha, A, B, &beta, C, CUDA_R_32F, alg, d, &b1, buf1)) break;
+            if (alg != CUSPARSE_SPGEMM_ALG1) {
+                const float frac = 0.2f;
+                if (cusparseSpGEMM_estimateMemory(hnd, N, N, &alpha, A, B, &beta, C, CUDA_R_32F, alg, d, frac, &b3, nullptr, nullptr)) break;
+                if (cudaMalloc(&buf3, b3 + 16) != cudaSuccess) break;
+                if (cusparseSpGEMM_estimateMemory(hnd, N, N, &alpha, A, B, &beta, C, CUDA_R_32F, alg, d, frac, &b3, buf3, &b2)) break;
+                cudaFree(buf3); buf3 = nullptr;
+            } else {
+                if (cusparseSpGEMM_compute(hnd, N, N, &alpha, A, B, &beta, C, CUDA_R_32F, alg, d, &b2, nullptr)) break;
+            }
+            if (cudaMalloc(&buf2, b2 + 16) != cudaSuccess) break;
+            if (cusparseSpGEMM_compute(hnd, N, N, &alpha, A, B, &beta, C, CUDA_R_32F, alg, d, &b2, buf2)) break;
+            int64_t cr, cc, cn;
+            if (cusparseSpMatGetSize(C, &cr, &cc, &cn)) break;
+            if (cudaMalloc(&c_ci, 4 * cn + 16) != cudaSuccess || cudaMalloc(&c_v, 4 * cn + 16) != cudaSuccess) break;
+            if (cusparseCsrSetPointers(C, c_rp, c_ci, c_v)) break;
+            if (cusparseSpGEMM_copy(hnd, N, N, &alpha, A, B, &beta, C, CUDA_R_32F, alg, d)) break;
+            cudaEventRecord(e1);
+            if (cudaEventSynchronize(e1) != cudaSuccess) break;
+            cudaEventElapsedTime(ms_out, e0, e1);
+            *nnz_out = cn;
+            if (verbose) printf("cusparse spgemm buffers: %.1f MB + %.1f MB\n", b1 / 1e6, b2 / 1e6);
+            rc = 0;
+        } while (0);
+        cudaGetLastError();
+        if (d) cusparseSpGEMM_destroyDescr(d);
+        if (C) cusparseDestroySpMat(C);
+        cudaFree(buf1); cudaFree(buf2); cudaFree(buf3); cudaFree(c_rp); cudaFree(c_ci); cudaFree(c_v);
+        return rc;
+    };
+    for (int a = 0; a < 3 && !used; a++) {
+        if (want_alg && alg_id[a] != want_alg) continue;
+        float ms = 0;
+        if (once(algs[a], &ms, &c_nnz, true) != 0) { fprintf(stderr, "cuSPARSE SpGEMM ALG%d failed (insufficient resources?)\n", alg_id[a]); continue; }
+        used = alg_id[a];
+        for (int r = 0; r < reps; r++) {
+            if (once(algs[a], &ms, &c_nnz, false) != 0) { used = 0; break; }
+            if (ms < best) best = ms;
+        }
     }
-    printf("CUSPARSE_SPGEMM_MS %.3f rows %lld nnz %lld c_nnz %lld\n", best, rows, nnz, c_nnz);
+    if (!used) { fprintf(stderr, "cuSPARSE SpGEMM: no algorithm completed\n"); return 1; }
+    printf("CUSPARSE_SPGEMM_MS %.3f rows %lld nnz %lld c_nnz %lld alg %d\n", best, rows, nnz, c_nnz, used);
     return 0;
 }
