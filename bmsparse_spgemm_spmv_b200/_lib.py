@@ -36,7 +36,7 @@ class View(C.Structure):
 class SpgemmInfo(C.Structure):
     _fields_ = [("symbolic_ms", C.c_float), ("numeric_ms", C.c_float), ("total_ms", C.c_float),
                 ("candidate_pairs", C.c_int64), ("surviving_pairs", C.c_int64), ("c_blocks", C.c_int64),
-                ("c_nnz", C.c_int64), ("numeric_path", C.c_int32)]
+                ("c_nnz", C.c_int64), ("numeric_path", C.c_int32), ("count_ms", C.c_float), ("fill_ms", C.c_float)]
 
 
 HALO_MAX = 8
@@ -56,7 +56,7 @@ class SpgemmOpts(C.Structure):
 # every symbol include/bmsparse_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["bmsp_abi_version", "bmsp_last_error", "bmsp_device_info", "bmsp_create_from_csr", "bmsp_create_from_coo",
            "bmsp_create_from_mtx", "bmsp_create_from_arrays", "bmsp_destroy", "bmsp_get", "bmsp_download",
-           "bmsp_to_coo", "bmsp_compare", "bmsp_spmv", "bmsp_spmv_host", "bmsp_spmv_bytes", "bmsp_spgemm", "bmsp_block_transpose",
+           "bmsp_to_coo", "bmsp_compare", "bmsp_to_csr", "bmsp_compare_csr", "bmsp_create_from_coo_ex", "bmsp_create_from_mtx_ex", "bmsp_spmv", "bmsp_spmv_host", "bmsp_spmv_bytes", "bmsp_spgemm", "bmsp_block_transpose",
            "bmsp_partition_block_rows", "bmsp_slice_block_rows", "bmsp_debug_pair_bitmap", "bmsp_spmv_halo", "bmsp_halo_push",
            "bmsp_halo_status", "bmsp_peer_alloc", "bmsp_peer_open", "bmsp_peer_close", "bmsp_peer_free"]
 

@@ -14,6 +14,8 @@
 #include <string>
 #include <cstring>
 #include <cstdlib>
+#include <cctype>
+#include <thread>
 
 namespace bmsp {
 
@@ -312,14 +314,9 @@ int bmsp_create_from_csr(int32_t rows, int32_t cols, int64_t nnz, const int32_t*
     return s;
 }
 
-int bmsp_create_from_coo(int32_t rows, int32_t cols, int64_t nnz, const int32_t* row_idx, const int32_t* col_idx,
-                         const double* vals, int32_t transposed, int32_t out_dtype, void* stream, bmsp_matrix_t* out) {
-    if (!out || rows < 0 || cols < 0 || nnz < 0 || (nnz > 0 && (!row_idx || !col_idx || !vals))) {
-        set_error("bmsp_create_from_coo: invalid argument");
-        return BMSP_ERR_INVALID;
-    }
-    // host: counting sort by row, then sort columns inside each row; values cast straight from double
-    // (bmSpMatrix.cu:136-157 casts the parsed double to valueType in one rounding)
+// host COO -> CSR (counting sort by row, columns sorted inside each row); duplicates summed when `merge`
+static int coo_to_matrix(int32_t rows, int32_t cols, int64_t nnz, const int32_t* row_idx, const int32_t* col_idx, const double* vals,
+                         int32_t transposed, int32_t out_dtype, int32_t flags, void* stream, bmsp_matrix_t* out) {
     std::vector<int32_t> rp((size_t)rows + 1, 0);
     for (int64_t i = 0; i < nnz; i++) {
         if (row_idx[i] < 0 || row_idx[i] >= rows) { set_error("row index outside [0, %d)", rows); return BMSP_ERR_RANGE; }
@@ -332,20 +329,60 @@ int bmsp_create_from_coo(int32_t rows, int32_t cols, int64_t nnz, const int32_t*
         for (int64_t i = 0; i < nnz; i++) perm[(size_t)cur[row_idx[i]]++] = i;
     }
     for (int32_t r = 0; r < rows; r++)
-        std::sort(perm.begin() + rp[r], perm.begin() + rp[r + 1], [&](int64_t a, int64_t b) { return col_idx[a] < col_idx[b]; });
+        std::stable_sort(perm.begin() + rp[r], perm.begin() + rp[r + 1], [&](int64_t a, int64_t b) { return col_idx[a] < col_idx[b]; });
     std::vector<int32_t> ci((size_t)nnz);
-    for (int64_t i = 0; i < nnz; i++) ci[i] = col_idx[perm[i]];
-    if (out_dtype == BMSP_F16) {
-        std::vector<__half> v((size_t)nnz);
-        for (int64_t i = 0; i < nnz; i++) v[i] = __double2half(vals[perm[i]]);
-        return bmsp_create_from_csr(rows, cols, nnz, rp.data(), ci.data(), v.data(), BMSP_F16, BMSP_HOST, transposed, BMSP_F16, stream, out);
+    std::vector<double> dv((size_t)nnz);
+    for (int64_t i = 0; i < nnz; i++) { ci[i] = col_idx[perm[i]]; dv[i] = vals[perm[i]]; }
+    int64_t n = nnz;
+    if (flags & BMSP_MERGE_DUPLICATES) {
+        // repeated (row, col) entries are summed in file order (what assembling a finite-element matrix means by them); the
+        // reference keeps them apart and corrupts its offsets, without this flag they are rejected
+        std::vector<int32_t> nrp((size_t)rows + 1, 0);
+        int64_t w = 0;
+        for (int32_t r = 0; r < rows; r++) {
+            for (int64_t i = rp[r]; i < rp[r + 1]; i++) {
+                if (i > rp[r] && ci[i] == ci[w - 1] && w > nrp[r]) dv[w - 1] += dv[i];
+                else { ci[w] = ci[i]; dv[w] = dv[i]; w++; }
+            }
+            nrp[r + 1] = (int32_t)w;
+        }
+        rp.swap(nrp); n = w;
     }
-    std::vector<float> v((size_t)nnz);
-    for (int64_t i = 0; i < nnz; i++) v[i] = (float)vals[perm[i]];
-    return bmsp_create_from_csr(rows, cols, nnz, rp.data(), ci.data(), v.data(), BMSP_F32, BMSP_HOST, transposed, out_dtype, stream, out);
+    if (out_dtype == BMSP_F16) {
+        std::vector<__half> v((size_t)n);
+        for (int64_t i = 0; i < n; i++) v[i] = __double2half(dv[i]);
+        return bmsp_create_from_csr(rows, cols, n, rp.data(), ci.data(), v.data(), BMSP_F16, BMSP_HOST, transposed, BMSP_F16, stream, out);
+    }
+    std::vector<float> v((size_t)n);
+    for (int64_t i = 0; i < n; i++) v[i] = (float)dv[i];
+    return bmsp_create_from_csr(rows, cols, n, rp.data(), ci.data(), v.data(), BMSP_F32, BMSP_HOST, transposed, out_dtype, stream, out);
 }
 
-int bmsp_create_from_mtx(const char* path, int32_t transposed, int32_t out_dtype, void* stream, bmsp_matrix_t* out) {
+int bmsp_create_from_coo_ex(int32_t rows, int32_t cols, int64_t nnz, const int32_t* row_idx, const int32_t* col_idx,
+                            const double* vals, int32_t transposed, int32_t out_dtype, int32_t flags, void* stream, bmsp_matrix_t* out) {
+    if (!out || rows < 0 || cols < 0 || nnz < 0 || (nnz > 0 && (!row_idx || !col_idx || !vals))) {
+        set_error("bmsp_create_from_coo: invalid argument");
+        return BMSP_ERR_INVALID;
+    }
+    // values cast straight from double (bmSpMatrix.cu:136-157 casts the parsed double to valueType in one rounding)
+    return coo_to_matrix(rows, cols, nnz, row_idx, col_idx, vals, transposed, out_dtype, flags, stream, out);
+}
+
+int bmsp_create_from_coo(int32_t rows, int32_t cols, int64_t nnz, const int32_t* row_idx, const int32_t* col_idx,
+                         const double* vals, int32_t transposed, int32_t out_dtype, void* stream, bmsp_matrix_t* out) {
+    return bmsp_create_from_coo_ex(rows, cols, nnz, row_idx, col_idx, vals, transposed, out_dtype, 0, stream, out);
+}
+
+// MatrixMarket coordinate files.  Banner rules follow cusp's reader (cusp/io/detail/matrix_market.inl:70-95): five tokens,
+// storage coordinate | array, type real | integer | pattern | complex, symmetry general | symmetric | skew-symmetric | hermitian.
+//   pattern            value 1 (:171)                       integer           parsed like real (:177-190)
+//   symmetric          off-diagonal entries mirrored (:257-279; bmSpMatrix.cu:113-149 does the same)
+//   skew-symmetric     mirrored with the sign flipped (cusp throws not_implemented :286-290; the reference's own reader would mirror it
+//                      with the SAME sign because "skew-symmetric" contains "symmetric", bmSpMatrix.cu:113-120)
+//   complex, hermitian, array storage: BMSP_ERR_UNSUPPORTED (a real-valued bmSpMatrix cannot hold them; cusp keeps only the real part)
+// Indices are checked against the size line (:222-235).  The body is parsed by all host cores: the text is cut at line ends into
+// one slice per thread (strtol / strtod, no streams).
+int bmsp_create_from_mtx_ex(const char* path, int32_t transposed, int32_t out_dtype, int32_t flags, void* stream, bmsp_matrix_t* out) {
     if (!path || !out) { set_error("bmsp_create_from_mtx: null argument"); return BMSP_ERR_INVALID; }
     std::ifstream f(path, std::ios::binary);
     if (!f) { set_error("cannot open %s", path); return BMSP_ERR_IO; }
@@ -355,28 +392,96 @@ int bmsp_create_from_mtx(const char* path, int32_t transposed, int32_t out_dtype
     auto line_end = [&](const char* q) { while (q < end && *q != '\n') q++; return q; };
     const char* le = line_end(p);
     std::string banner(p, le);
-    // banner handling follows bmSpMatrix.cu:113-120 ("symmetric" anywhere in the first line) and adds
-    // "pattern" (value 1) which the reference would mis-parse
-    bool symmetric = banner.find("symmetric") != std::string::npos;
-    bool pattern = banner.find("pattern") != std::string::npos;
+    std::vector<std::string> tok;
+    {
+        size_t i = 0;
+        while (i < banner.size()) {
+            while (i < banner.size() && isspace((unsigned char)banner[i])) i++;
+            size_t j = i;
+            while (j < banner.size() && !isspace((unsigned char)banner[j])) j++;
+            if (j > i) tok.push_back(banner.substr(i, j - i));
+            i = j;
+        }
+        for (auto& t : tok) for (auto& ch : t) ch = (char)tolower((unsigned char)ch);
+    }
+    bool symmetric = false, skew = false, pattern = false;
+    if (tok.size() == 5 && tok[0] == "%%matrixmarket") {
+        if (tok[1] != "matrix") { set_error("%s: invalid MatrixMarket banner", path); return BMSP_ERR_IO; }
+        if (tok[2] == "array") { set_error("%s: array storage is not supported (coordinate files only)", path); return BMSP_ERR_UNSUPPORTED; }
+        if (tok[2] != "coordinate") { set_error("%s: invalid MatrixMarket storage format [%s]", path, tok[2].c_str()); return BMSP_ERR_IO; }
+        if (tok[3] == "complex") { set_error("%s: complex matrices are not supported", path); return BMSP_ERR_UNSUPPORTED; }
+        if (tok[3] == "pattern") pattern = true;
+        else if (tok[3] != "real" && tok[3] != "integer") { set_error("%s: invalid MatrixMarket data type [%s]", path, tok[3].c_str()); return BMSP_ERR_IO; }
+        if (tok[4] == "hermitian") { set_error("%s: hermitian matrices are not supported", path); return BMSP_ERR_UNSUPPORTED; }
+        if (tok[4] == "symmetric") symmetric = true;
+        else if (tok[4] == "skew-symmetric") skew = true;
+        else if (tok[4] != "general") { set_error("%s: invalid MatrixMarket symmetry [%s]", path, tok[4].c_str()); return BMSP_ERR_IO; }
+    } else {
+        // no well-formed banner: the reference's rule -- "symmetric" anywhere in the first line (bmSpMatrix.cu:113-120)
+        symmetric = banner.find("symmetric") != std::string::npos;
+        pattern = banner.find("pattern") != std::string::npos;
+        if (!banner.empty() && banner[0] != '%') le = p - 1;          // the first line already is the size line
+    }
     p = le < end ? le + 1 : end;
-    while (p < end && *p == '%') { le = line_end(p); p = le < end ? le + 1 : end; }
+    while (p < end && (*p == '%' || *p == '\n' || *p == '\r')) { le = line_end(p); p = le < end ? le + 1 : end; }
     char* q = nullptr;
     long nr = strtol(p, &q, 10); p = q;
     long nc = strtol(p, &q, 10); p = q;
     long long nl = strtoll(p, &q, 10); p = q;
-    if (nr <= 0 || nc <= 0 || nl < 0) { set_error("%s: bad size line", path); return BMSP_ERR_IO; }
-    std::vector<int32_t> r, c; std::vector<double> v;
-    r.reserve((size_t)nl * (symmetric ? 2 : 1)); c.reserve(r.capacity()); v.reserve(r.capacity());
-    for (long long l = 0; l < nl; l++) {
-        long i = strtol(p, &q, 10); if (q == p) { set_error("%s: truncated at entry %lld", path, l); return BMSP_ERR_IO; } p = q;
-        long j = strtol(p, &q, 10); if (q == p) { set_error("%s: truncated at entry %lld", path, l); return BMSP_ERR_IO; } p = q;
-        double x = 1.0;
-        if (!pattern) { x = strtod(p, &q); if (q == p) { set_error("%s: missing value at entry %lld", path, l); return BMSP_ERR_IO; } p = q; }
-        r.push_back((int32_t)(i - 1)); c.push_back((int32_t)(j - 1)); v.push_back(x);
-        if (symmetric && i != j) { r.push_back((int32_t)(j - 1)); c.push_back((int32_t)(i - 1)); v.push_back(x); }
+    if (nr <= 0 || nc <= 0 || nl < 0 || nr > 0x7FFFFFFFl || nc > 0x7FFFFFFFl) { set_error("%s: bad size line", path); return BMSP_ERR_IO; }
+    le = line_end(p); p = le < end ? le + 1 : end;
+    // slices of whole lines, one per thread
+    int nth = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    if ((end - p) < (1 << 20)) nth = 1;
+    std::vector<const char*> cut((size_t)nth + 1);
+    cut[0] = p; cut[nth] = end;
+    for (int t = 1; t < nth; t++) { const char* c = p + (end - p) * t / nth; c = line_end(c); cut[t] = c < end ? c + 1 : end; }
+    struct Part { std::vector<int32_t> r, c; std::vector<double> v; int err = 0; long long lines = 0; };
+    std::vector<Part> parts((size_t)nth);
+    auto parse = [&](int t) {
+        Part& P = parts[(size_t)t];
+        const char* s = cut[t]; const char* e = cut[t + 1];
+        P.r.reserve((size_t)((e - s) / 12 + 16)); P.c.reserve(P.r.capacity()); P.v.reserve(P.r.capacity());
+        char* qq = nullptr;
+        while (s < e) {
+            while (s < e && (*s == ' ' || *s == '\t' || *s == '\r' || *s == '\n')) s++;
+            if (s >= e) break;
+            if (*s == '%') { while (s < e && *s != '\n') s++; continue; }
+            long i = strtol(s, &qq, 10); if (qq == s) { P.err = BMSP_ERR_IO; return; } s = qq;
+            long j = strtol(s, &qq, 10); if (qq == s) { P.err = BMSP_ERR_IO; return; } s = qq;
+            double x = 1.0;
+            if (!pattern) { x = strtod(s, &qq); if (qq == s) { P.err = BMSP_ERR_IO; return; } s = qq; }
+            if (i < 1 || i > nr || j < 1 || j > nc) { P.err = BMSP_ERR_RANGE; return; }
+            P.lines++;
+            P.r.push_back((int32_t)(i - 1)); P.c.push_back((int32_t)(j - 1)); P.v.push_back(x);
+            if ((symmetric || skew) && i != j) { P.r.push_back((int32_t)(j - 1)); P.c.push_back((int32_t)(i - 1)); P.v.push_back(skew ? -x : x); }
+            while (s < e && *s != '\n') s++;
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nth; t++) th.emplace_back(parse, t);
+        parse(0);
+        for (auto& t : th) t.join();
     }
-    return bmsp_create_from_coo((int32_t)nr, (int32_t)nc, (int64_t)r.size(), r.data(), c.data(), v.data(), transposed, out_dtype, stream, out);
+    size_t total = 0; long long lines = 0;
+    for (auto& P : parts) {
+        if (P.err == BMSP_ERR_RANGE) { set_error("%s: index outside the %ld x %ld matrix", path, nr, nc); return BMSP_ERR_RANGE; }
+        if (P.err) { set_error("%s: malformed entry line", path); return BMSP_ERR_IO; }
+        total += P.r.size(); lines += P.lines;
+    }
+    std::vector<int32_t> r(total), c(total); std::vector<double> v(total);
+    size_t w = 0;
+    for (auto& P : parts) {
+        std::copy(P.r.begin(), P.r.end(), r.begin() + w); std::copy(P.c.begin(), P.c.end(), c.begin() + w); std::copy(P.v.begin(), P.v.end(), v.begin() + w);
+        w += P.r.size();
+    }
+    if (lines != nl) { set_error("%s: %lld entry lines, the size line announces %lld", path, lines, nl); return BMSP_ERR_IO; }
+    return coo_to_matrix((int32_t)nr, (int32_t)nc, (int64_t)total, r.data(), c.data(), v.data(), transposed, out_dtype, flags, stream, out);
+}
+
+int bmsp_create_from_mtx(const char* path, int32_t transposed, int32_t out_dtype, void* stream, bmsp_matrix_t* out) {
+    return bmsp_create_from_mtx_ex(path, transposed, out_dtype, 0, stream, out);
 }
 
 int bmsp_block_transpose(bmsp_matrix_t A, int32_t out_dtype, void* stream, bmsp_matrix_t* At) {

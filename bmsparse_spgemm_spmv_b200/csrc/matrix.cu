@@ -330,41 +330,235 @@ extern "C" int bmsp_to_coo(bmsp_matrix_t m, int32_t* rows, int32_t* cols, float*
     return BMSP_OK;
 }
 
+// ------------------------------------------------------------------------------------ bmSparse -> CSR on the device
+// The blocks of a block row are already in ascending block column and a bitmap is row-major inside a block, so CSR order is an
+// 8-way merge in reverse: entry (r, c) of block b goes to row_ptr[r] + (cells of row r in the earlier blocks of the block row) +
+// (cells of row r left of c in this block).  Pass 1 counts the cells per matrix row (one thread per block), a scan gives row_ptr,
+// pass 2 runs one warp per block row: lanes <-> blocks, 32 at a time; the eight per-row counts of a block travel as two 64-bit
+// words of four 16-bit fields through one warp scan each.
+__global__ void csr_count_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ bmps, int64_t nblk, int32_t rows,
+                                 uint32_t* __restrict__ row_cnt) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const uint64_t bmp = bmps[b];
+    const int64_t r0 = (int64_t)(keys[b] >> 32) * 8;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint32_t c = __popc((uint32_t)(bmp >> (56 - 8 * r)) & 0xFFu);
+        if (c && r0 + r < rows) atomicAdd(row_cnt + r0 + r, c);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) csr_fill_kernel(const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol, const uint64_t* __restrict__ bmps,
+                                                       const uint64_t* __restrict__ offsets, const T* __restrict__ values, int32_t nbr, int32_t rows,
+                                                       const uint32_t* __restrict__ row_ptr, int32_t* __restrict__ col_idx, float* __restrict__ vals) {
+    const int lane = threadIdx.x & 31;
+    const int br = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (br >= nbr) return;
+    uint32_t base[8];                     // next free slot of each of the block row's eight matrix rows (warp-uniform)
+#pragma unroll
+    for (int r = 0; r < 8; r++) base[r] = (int64_t)br * 8 + r < rows ? row_ptr[(int64_t)br * 8 + r] : 0u;
+    for (int b0 = brp[br]; b0 < brp[br + 1]; b0 += 32) {
+        const int b = b0 + lane;
+        const bool valid = b < brp[br + 1];
+        const uint64_t bmp = valid ? bmps[b] : 0ull;
+        uint64_t lo = 0, hi = 0;          // per-row counts, 16-bit fields: rows 0-3 in lo, 4-7 in hi
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            lo |= (uint64_t)__popc((uint32_t)(bmp >> (56 - 8 * r)) & 0xFFu) << (16 * r);
+            hi |= (uint64_t)__popc((uint32_t)(bmp >> (24 - 8 * r)) & 0xFFu) << (16 * r);
+        }
+        uint64_t ilo = lo, ihi = hi;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t tl = __shfl_up_sync(0xffffffffu, ilo, o), th = __shfl_up_sync(0xffffffffu, ihi, o);
+            if (lane >= o) { ilo += tl; ihi += th; }
+        }
+        const uint64_t elo = ilo - lo, ehi = ihi - hi;             // exclusive: cells of each row in the earlier blocks of this chunk
+        if (valid) {
+            uint64_t k = offsets[b];
+            const int32_t c0 = bcol[b] * 8;
+            uint64_t rem = bmp;
+            uint32_t in_row[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            while (rem) {
+                const int p = __clzll((long long)rem);
+                rem &= ~(0x8000000000000000ull >> p);
+                const int r = p >> 3;
+                const uint32_t ex = (uint32_t)(((r < 4 ? elo : ehi) >> (16 * (r & 3))) & 0xFFFFu);
+                uint32_t slot = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) if (q == r) slot = base[q] + ex + in_row[q]++;
+                col_idx[slot] = c0 + (p & 7);
+                vals[slot] = val_to_f32(values[k++]);
+            }
+        }
+        const uint64_t tlo = __shfl_sync(0xffffffffu, ilo, 31), thi = __shfl_sync(0xffffffffu, ihi, 31);
+#pragma unroll
+        for (int r = 0; r < 4; r++) { base[r] += (uint32_t)((tlo >> (16 * r)) & 0xFFFFu); base[4 + r] += (uint32_t)((thi >> (16 * r)) & 0xFFFFu); }
+    }
+}
+
+// device CSR of m into caller-provided device arrays (row_ptr: rows + 1)
+static int to_csr_device(bmsp_matrix_s* m, int32_t* d_rp, int32_t* d_ci, float* d_v, cudaStream_t st) {
+    if (m->transposed) { set_error("bmsp_to_csr: matrix is in transposed-operand form (bmsp_block_transpose first)"); return BMSP_ERR_UNSUPPORTED; }
+    BMSP_CUDA(cudaMemsetAsync(d_rp, 0, sizeof(int32_t) * ((size_t)m->rows + 1), st));
+    if (m->nblk == 0) return BMSP_OK;
+    csr_count_kernel<<<(unsigned)ceil_div(m->nblk, 256), 256, 0, st>>>(m->keys, m->bmps, m->nblk, m->rows, (uint32_t*)d_rp);
+    BMSP_KERNEL_CHECK();
+    BMSP_TRY(exclusive_scan_u32((const uint32_t*)d_rp, (uint32_t*)d_rp, m->rows, st));
+    const unsigned grid = (unsigned)ceil_div(m->nbr, 8);
+    if (m->dtype == BMSP_F16)
+        csr_fill_kernel<__half><<<grid, 256, 0, st>>>(m->brp, m->bcol, m->bmps, m->offsets, (const __half*)m->values, m->nbr, m->rows, (const uint32_t*)d_rp, d_ci, d_v);
+    else
+        csr_fill_kernel<float><<<grid, 256, 0, st>>>(m->brp, m->bcol, m->bmps, m->offsets, (const float*)m->values, m->nbr, m->rows, (const uint32_t*)d_rp, d_ci, d_v);
+    BMSP_KERNEL_CHECK();
+    return BMSP_OK;
+}
+
+extern "C" int bmsp_to_csr(bmsp_matrix_t m, int32_t* row_ptr, int32_t* col_idx, float* vals, int32_t mem, void* stream) {
+    if (!m || !row_ptr || (m->nnz > 0 && (!col_idx || !vals))) { set_error("bmsp_to_csr: null argument"); return BMSP_ERR_INVALID; }
+    if (m->nnz > 0x7FFFFFFFll) { set_error("bmsp_to_csr: %lld values exceed int32 row pointers", (long long)m->nnz); return BMSP_ERR_TOO_LARGE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    touch(m, st);
+    if (mem == BMSP_DEVICE) return to_csr_device(m, row_ptr, col_idx, vals, st);
+    int32_t *d_rp = nullptr, *d_ci = nullptr; float* d_v = nullptr;
+    BMSP_TRY(dev_alloc_t(&d_rp, (size_t)m->rows + 2, st));
+    BMSP_TRY(dev_alloc_t(&d_ci, (size_t)m->nnz + 1, st));
+    BMSP_TRY(dev_alloc_t(&d_v, (size_t)m->nnz + 1, st));
+    int s = to_csr_device(m, d_rp, d_ci, d_v, st);
+    if (s == BMSP_OK) {
+        cudaError_t e = cudaMemcpyAsync(row_ptr, d_rp, sizeof(int32_t) * ((size_t)m->rows + 1), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && m->nnz) e = cudaMemcpyAsync(col_idx, d_ci, sizeof(int32_t) * (size_t)m->nnz, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && m->nnz) e = cudaMemcpyAsync(vals, d_v, sizeof(float) * (size_t)m->nnz, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) s = cuda_fail(e, "bmsp_to_csr: copy out", __FILE__, __LINE__);
+    }
+    dev_free(d_rp, st); dev_free(d_ci, st); dev_free(d_v, st);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------ compare on the device
+// Both sides as CSR (columns ascending in every row): one thread per matrix row merges the two column lists -- no sort.  Counts
+// and error sums are reduced per CTA, then with one atomic per CTA (doubles: the mean is order-dependent only in the last bits).
+__global__ void __launch_bounds__(256) compare_rows_kernel(int32_t rows, const int32_t* __restrict__ a_rp, const int32_t* __restrict__ a_ci,
+                                                           const float* __restrict__ a_v, const int32_t* __restrict__ b_rp,
+                                                           const int32_t* __restrict__ b_ci, const float* __restrict__ b_v,
+                                                           unsigned long long* __restrict__ counts, double* __restrict__ sums) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long only_a = 0, only_b = 0, common = 0;
+    double sum = 0.0, mx = 0.0;
+    if (r < rows) {
+        int i = a_rp[r], j = b_rp[r];
+        const int ie = a_rp[r + 1], je = b_rp[r + 1];
+        while (i < ie || j < je) {
+            const int ca = i < ie ? a_ci[i] : 0x7FFFFFFF, cb = j < je ? b_ci[j] : 0x7FFFFFFF;
+            if (ca < cb) { only_a++; i++; }
+            else if (cb < ca) { only_b++; j++; }
+            else {
+                const double e = (double)b_v[j], g = (double)a_v[i];
+                const double rel = fabs(e - g) / fmax(fabs(e), 1e-8);       // the reference's metric, bmSpMatrix.cu:418
+                sum += rel; mx = fmax(mx, rel); common++;
+                i++; j++;
+            }
+        }
+    }
+    __shared__ unsigned long long s_c[3];
+    __shared__ double s_sum;
+    __shared__ unsigned long long s_mx;
+    if (threadIdx.x == 0) { s_c[0] = s_c[1] = s_c[2] = 0; s_sum = 0.0; s_mx = 0ull; }
+    __syncthreads();
+    for (int o = 16; o; o >>= 1) {
+        only_a += __shfl_xor_sync(0xffffffffu, only_a, o); only_b += __shfl_xor_sync(0xffffffffu, only_b, o);
+        common += __shfl_xor_sync(0xffffffffu, common, o); sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_c[0], only_a); atomicAdd(&s_c[1], only_b); atomicAdd(&s_c[2], common); atomicAdd(&s_sum, sum);
+        atomicMax(&s_mx, (unsigned long long)__double_as_longlong(mx));       // non-negative doubles order like their bit patterns
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_c[0]) atomicAdd(counts + 0, s_c[0]);
+        if (s_c[1]) atomicAdd(counts + 1, s_c[1]);
+        if (s_c[2]) atomicAdd(counts + 2, s_c[2]);
+        if (s_sum != 0.0) atomicAdd(sums, s_sum);
+        if (s_mx) atomicMax(counts + 3, s_mx);
+    }
+}
+
+extern "C" int bmsp_compare_csr(bmsp_matrix_t m, const int32_t* row_ptr, const int32_t* col_idx, const float* vals, int32_t mem, void* stream,
+                                int64_t* only_in_m, int64_t* only_in_csr, double* mean_rel_err, double* max_rel_err) {
+    if (!m || !row_ptr) { set_error("bmsp_compare_csr: null argument"); return BMSP_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    touch(m, st);
+    int32_t *a_rp = nullptr, *a_ci = nullptr, *b_rp = nullptr, *b_ci = nullptr; float *a_v = nullptr, *b_v = nullptr;
+    unsigned long long* acc = nullptr;
+    int s = BMSP_OK;
+    auto cleanup = [&]() { dev_free(a_rp, st); dev_free(a_ci, st); dev_free(a_v, st); dev_free(acc, st); if (mem != BMSP_DEVICE) { dev_free(b_rp, st); dev_free(b_ci, st); dev_free(b_v, st); } };
+#define CMP_TRY(x) do { s = (x); if (s != BMSP_OK) { cleanup(); return s; } } while (0)
+#define CMP_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { cleanup(); return cuda_fail(e__, #x, __FILE__, __LINE__); } } while (0)
+    CMP_TRY(dev_alloc_t(&a_rp, (size_t)m->rows + 2, st));
+    CMP_TRY(dev_alloc_t(&a_ci, (size_t)m->nnz + 1, st));
+    CMP_TRY(dev_alloc_t(&a_v, (size_t)m->nnz + 1, st));
+    CMP_TRY(dev_alloc_t(&acc, 8, st));
+    CMP_CUDA(cudaMemsetAsync(acc, 0, 8 * sizeof(unsigned long long), st));
+    CMP_TRY(to_csr_device(m, a_rp, a_ci, a_v, st));
+    if (mem == BMSP_DEVICE) { b_rp = const_cast<int32_t*>(row_ptr); b_ci = const_cast<int32_t*>(col_idx); b_v = const_cast<float*>(vals); }
+    else {
+        const int64_t n = row_ptr[m->rows];
+        CMP_TRY(dev_alloc_t(&b_rp, (size_t)m->rows + 2, st));
+        CMP_TRY(dev_alloc_t(&b_ci, (size_t)n + 1, st));
+        CMP_TRY(dev_alloc_t(&b_v, (size_t)n + 1, st));
+        CMP_CUDA(cudaMemcpyAsync(b_rp, row_ptr, sizeof(int32_t) * ((size_t)m->rows + 1), cudaMemcpyHostToDevice, st));
+        if (n) {
+            CMP_CUDA(cudaMemcpyAsync(b_ci, col_idx, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+            CMP_CUDA(cudaMemcpyAsync(b_v, vals, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+        }
+    }
+    if (m->rows > 0) {
+        compare_rows_kernel<<<(unsigned)ceil_div(m->rows, 256), 256, 0, st>>>(m->rows, a_rp, a_ci, a_v, b_rp, b_ci, b_v, acc, reinterpret_cast<double*>(acc + 4));
+        CMP_CUDA(cudaGetLastError());
+    }
+    unsigned long long h[8];
+    CMP_CUDA(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CMP_CUDA(cudaStreamSynchronize(st));
+    double sum, mx;
+    memcpy(&sum, &h[4], 8); memcpy(&mx, &h[3], 8);
+    if (only_in_m) *only_in_m = (int64_t)h[0];
+    if (only_in_csr) *only_in_csr = (int64_t)h[1];
+    if (mean_rel_err) *mean_rel_err = h[2] ? sum / (double)h[2] : 0.0;
+    if (max_rel_err) *max_rel_err = mx;
+    cleanup();
+    return BMSP_OK;
+#undef CMP_TRY
+#undef CMP_CUDA
+}
+
 extern "C" int bmsp_compare(bmsp_matrix_t m, int64_t nnz, const int32_t* rows, const int32_t* cols, const float* vals,
                             int64_t* only_in_m, int64_t* only_in_coo, double* mean_rel_err, double* max_rel_err) {
     if (!m || (nnz > 0 && (!rows || !cols || !vals))) { set_error("bmsp_compare: null argument"); return BMSP_ERR_INVALID; }
-    // decode on the device, merge on the host (test utility, like the reference's host walk :398-428)
-    std::vector<int32_t> r((size_t)m->nnz), c((size_t)m->nnz);
-    std::vector<float> v((size_t)m->nnz);
-    if (m->nnz) BMSP_TRY(bmsp_to_coo(m, r.data(), c.data(), v.data()));
-    std::vector<int64_t> pa((size_t)m->nnz), pb((size_t)nnz);
-    for (int64_t i = 0; i < m->nnz; i++) pa[i] = i;
-    for (int64_t i = 0; i < nnz; i++) pb[i] = i;
-    std::sort(pa.begin(), pa.end(), [&](int64_t x, int64_t y) { return r[x] != r[y] ? r[x] < r[y] : c[x] < c[y]; });
-    std::sort(pb.begin(), pb.end(), [&](int64_t x, int64_t y) { return rows[x] != rows[y] ? rows[x] < rows[y] : cols[x] < cols[y]; });
-    int64_t i = 0, j = 0, oa = 0, ob = 0, common = 0;
-    double sum = 0, mx = 0;
-    const double eps = 1e-8;
-    while (i < m->nnz || j < nnz) {
-        int cmp;
-        if (i >= m->nnz) cmp = 1;
-        else if (j >= nnz) cmp = -1;
-        else {
-            int64_t a = pa[i], b = pb[j];
-            cmp = r[a] != rows[b] ? (r[a] < rows[b] ? -1 : 1) : (c[a] != cols[b] ? (c[a] < cols[b] ? -1 : 1) : 0);
-        }
-        if (cmp < 0) { oa++; i++; }
-        else if (cmp > 0) { ob++; j++; }
-        else {
-            double e = vals[pb[j]], g = v[pa[i]];
-            double rel = std::fabs(e - g) / std::max(std::fabs(e), eps);
-            sum += rel; mx = std::max(mx, rel); common++;
-            i++; j++;
-        }
+    // the COO (any order) becomes CSR on the host -- counting sort by row, columns sorted inside each row -- and the comparison
+    // itself runs on the device (bmsp_compare_csr); entries outside the matrix count as "only in the COO"
+    std::vector<int32_t> rp((size_t)m->rows + 1, 0);
+    int64_t outside = 0;
+    for (int64_t i = 0; i < nnz; i++) {
+        if (rows[i] < 0 || rows[i] >= m->rows) { outside++; continue; }
+        rp[(size_t)rows[i] + 1]++;
     }
-    if (only_in_m) *only_in_m = oa;
-    if (only_in_coo) *only_in_coo = ob;
-    if (mean_rel_err) *mean_rel_err = common ? sum / common : 0.0;
-    if (max_rel_err) *max_rel_err = mx;
+    for (int32_t r = 0; r < m->rows; r++) rp[r + 1] += rp[r];
+    const int64_t n_in = rp[m->rows];
+    std::vector<int64_t> perm((size_t)n_in);
+    {
+        std::vector<int32_t> cur(rp.begin(), rp.end() - 1);
+        for (int64_t i = 0; i < nnz; i++) if (rows[i] >= 0 && rows[i] < m->rows) perm[(size_t)cur[rows[i]]++] = i;
+    }
+    for (int32_t r = 0; r < m->rows; r++)
+        std::sort(perm.begin() + rp[r], perm.begin() + rp[r + 1], [&](int64_t a, int64_t b) { return cols[a] < cols[b]; });
+    std::vector<int32_t> ci((size_t)n_in); std::vector<float> v((size_t)n_in);
+    for (int64_t i = 0; i < n_in; i++) { ci[i] = cols[perm[i]]; v[i] = vals[perm[i]]; }
+    int64_t ob = 0;
+    BMSP_TRY(bmsp_compare_csr(m, rp.data(), ci.data(), v.data(), BMSP_HOST, m->last_stream, only_in_m, &ob, mean_rel_err, max_rel_err));
+    if (only_in_coo) *only_in_coo = ob + outside;
     return BMSP_OK;
 }

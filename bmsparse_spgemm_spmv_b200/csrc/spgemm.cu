@@ -32,7 +32,7 @@ constexpr int QSLOTS = 192;   // per-warp queue: 64 pairs (uint2) + 32 staged Pa
 struct GemmArgs {
     const int32_t* a_brp; const int32_t* a_bcol; const uint64_t* a_bmps; const uint8_t* a_kmask; const uint64_t* a_off; const __half* a_val;
     const int32_t* b_brp; const int32_t* b_bcol; const uint64_t* b_bmps; const uint8_t* b_kmask; const uint64_t* b_off; const __half* b_val;
-    const uint4* b_pm;         // packed per-B-block metadata {bitmap lo, bitmap hi, block column, value offset}: one sector per surviving pair
+    const uint4* b_pm;         // packed per-B-block records, two uint4 each: {bitmap lo, bitmap hi, block column, value offset}, {first 8 values}
     const int2* rowinfo;       // per A block row: x = first C block column of the bit set (multiple of 32), y = words
     int32_t row_begin, row_end;
     int32_t G;                 // lanes cooperating on one A block (power of two <= 32)
@@ -101,12 +101,20 @@ __global__ void pair_bitmap_test_kernel(const uint64_t* a, const uint64_t* bt, u
     if (i < n) out[i] = pair_bitmap(a[i], bt[i]);
 }
 
+// One 32-byte record (= one DRAM sector) per B block: {bitmap lo, bitmap hi, block column, value offset} + its first eight values.
+// A surviving pair of a sparse-block product (uniform random, R-MAT: ~1 value per block) then costs ONE random sector for
+// everything it needs from B -- column, bitmap and values -- instead of three (b_bcol, the packed metadata, b_val).
 __global__ void pack_meta_kernel(const uint64_t* __restrict__ bmps, const int32_t* __restrict__ bcol, const uint64_t* __restrict__ off,
-                                 uint4* __restrict__ pm, int64_t n) {
+                                 const __half* __restrict__ val, int64_t nnz, uint4* __restrict__ pm, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint64_t b = bmps[i];
-    pm[i] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)bcol[i], (uint32_t)off[i]);
+    const uint64_t b = bmps[i], o = off[i];
+    pm[2 * i] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)bcol[i], (uint32_t)o);
+    unsigned short h[8];
+    const int cnt = __popcll(b);
+#pragma unroll
+    for (int k = 0; k < 8; k++) h[k] = (k < cnt && (int64_t)o + k < nnz) ? __half_as_ushort(val[o + k]) : (unsigned short)0;
+    pm[2 * i + 1] = make_uint4(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16), h[4] | ((uint32_t)h[5] << 16), h[6] | ((uint32_t)h[7] << 16));
 }
 
 // P0: warp per A block row (grid-stride): candidate pairs, and the span [jmin, jmax] of C block columns.  The statistics are
@@ -216,14 +224,20 @@ __device__ __forceinline__ int local_row(const int* bounds, int nr, int v) {
 // the global loads a surviving pair starts with, kept apart from the work on them so that the scalar NUMERIC pass can have two
 // pairs' loads in flight per thread before it touches the first result (A/B on one box: U1M numeric 10.65 -> 9.55 ms, R-MAT-18
 // 146 -> 109 ms; the same batching in FILL and in the 8-lanes-per-pair walk cost more in registers than it hid in latency)
-struct PairIn { uint4 pm; uint64_t abmp; uint32_t aoff; };
+struct PairIn { uint4 pm; uint4 bv8; uint64_t abmp; uint32_t aoff; };
 template <int MODE>
 __device__ __forceinline__ PairIn load_pair(const GemmArgs& g, int a, int b) {
     PairIn in;
-    in.pm = __ldg(g.b_pm + b);
+    in.pm = __ldg(g.b_pm + 2 * (int64_t)b);
+    in.bv8 = MODE == MODE_FILL ? make_uint4(0, 0, 0, 0) : __ldg(g.b_pm + 2 * (int64_t)b + 1);     // same sector
     in.abmp = g.a_bmps[a];
     in.aoff = MODE == MODE_FILL ? 0u : (uint32_t)g.a_off[a];
     return in;
+}
+// value k (< 8) of a B block out of its record's inline copy
+__device__ __forceinline__ float inline_val(const uint4& v, int k) {
+    const uint32_t w = (k & 4) ? ((k & 2) ? v.w : v.z) : ((k & 2) ? v.y : v.x);
+    return __half2float(__ushort_as_half((unsigned short)((k & 1) ? (w >> 16) : (w & 0xFFFFu))));
 }
 
 template <int MODE>
@@ -243,6 +257,7 @@ __device__ __forceinline__ void apply_pair(const GemmArgs& g, const RowCtx& r, i
     } else {
         const __half* av = g.a_val + in.aoff;
         const __half* bv = g.b_val + pm.w;
+        const bool b_inline = __popcll(bbmp) <= 8;               // the record carries the block's values
         uint64_t cb; float* dst;
         if (r.acc) { cb = r.cbmp[c]; dst = r.acc + r.coff[c]; }
         else { cb = g.c_bmps[r.c0 + c]; dst = g.c_val + g.c_off[r.c0 + c]; }
@@ -262,7 +277,8 @@ __device__ __forceinline__ void apply_pair(const GemmArgs& g, const RowCtx& r, i
             while (hits) {
                 const int q = __clzll((long long)hits);
                 hits &= ~(0x8000000000000000ull >> q);
-                const float bval = __half2float(bv[rank64(bbmp, q)]);
+                const int kb = rank64(bbmp, q);
+                const float bval = b_inline ? inline_val(in.bv8, kb) : __half2float(bv[kb]);
                 atomicAdd(dst + rank64(cb, rr * 8 + (q >> 3)), aval * bval);
             }
         }
@@ -359,7 +375,7 @@ __device__ __forceinline__ void drain(const GemmArgs& g, const RowCtx& r, const 
 // tests one aligned 32-bit word of B's inner-dimension masks (kmask) against the replicated mask of its A block.
 // Survivors set their C block column in the row's bit set; with LIST they are also appended to the row's segment
 // of the global pair list (one shared cursor bump per warp and step).
-template <bool LIST, bool STATS>
+template <bool LIST, bool STATS, bool BITS = true>
 __device__ __forceinline__ void enumerate_vec(const GemmArgs& g, const RowCtx& r, uint2* list, uint32_t* s_cursor,
                                               unsigned long long& n_cand, uint32_t& n_surv) {
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
@@ -413,7 +429,7 @@ __device__ __forceinline__ void enumerate_vec(const GemmArgs& g, const RowCtx& r
                         if ((nz >> (8 * i)) & 1u) list[base + p4[i]] = make_uint2((uint32_t)a, (uint32_t)(bb + i));
                 }
             }
-            while (rem) {
+            while (BITS && rem) {
                 const int i = (__ffs(rem) - 1) >> 3;
                 rem &= ~(0xFFu << (8 * i));
                 const int j = g.b_bcol[bb + i] - jb;
@@ -630,7 +646,16 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
             if (cfit) for (int c = tid; c < ccount; c += T) r.cbmp[c] = 0;
             __syncthreads();
             uint32_t ns = 0;
-            enumerate_vec<true, false>(g, r, list, s_cursor, n_cand, ns);     // bits + pair list
+            // pair list only: a survivor's C block column comes with its packed B record (one sector, fetched here for the first time
+            // and again -- from L2 -- by the pair pass below) instead of a separate random read of b_bcol per survivor
+            enumerate_vec<true, false, false>(g, r, list, s_cursor, n_cand, ns);
+            __syncthreads();
+            for (uint32_t e = tid; e < nsurv; e += T) {
+                const uint2 pr = list[e];
+                const int rl = local_row(r.abr, r.nr, (int)pr.x);
+                const int j = (int)__ldg(&g.b_pm[2 * (int64_t)pr.y].z) - r.jb[rl];
+                atomicOr(&r.bitset[r.wo[rl] + (j >> 5)], 1u << (j & 31));
+            }
             __syncthreads();
             rank_words(r.bitset, r.wrank, nwords, s_tmp);
             for (uint32_t e = tid; e < nsurv; e += T) { const uint2 pr = list[e]; process_pair<MODE_FILL>(g, r, (int)pr.x, (int)pr.y); }
@@ -847,7 +872,7 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     BMSP_CUDA(cudaGetDevice(&dev));
     BMSP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};       // start, after FILL, end, after COUNT
     if (verbose) for (auto& e : ev) BMSP_CUDA(cudaEventCreate(&e));
     if (verbose) BMSP_CUDA(cudaEventRecord(ev[0], st));
 
@@ -940,8 +965,9 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     if (G > T) G = T;
 
     if (!Bt->pmeta && Bt->nblk > 0) {      // built once per B operand, reused by later products
-        SG_TRY(dev_alloc((void**)&Bt->pmeta, sizeof(uint4) * (size_t)Bt->nblk, st));
-        pack_meta_kernel<<<(unsigned)ceil_div(Bt->nblk, 256), 256, 0, st>>>(Bt->bmps, Bt->bcol, Bt->offsets, (uint4*)Bt->pmeta, Bt->nblk);
+        SG_TRY(dev_alloc((void**)&Bt->pmeta, 2 * sizeof(uint4) * (size_t)Bt->nblk, st));
+        pack_meta_kernel<<<(unsigned)ceil_div(Bt->nblk, 256), 256, 0, st>>>(Bt->bmps, Bt->bcol, Bt->offsets, (const __half*)Bt->values, Bt->nnz,
+                                                                          (uint4*)Bt->pmeta, Bt->nblk);
         SG_CUDA(cudaGetLastError());
     }
     GemmArgs g;
@@ -981,6 +1007,7 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
         SG_CUDA(cudaStreamSynchronize(st));
         c_size = tot[0]; n_surv = tot[1];
     }
+    if (verbose) SG_CUDA(cudaEventRecord(ev[3], st));
     unsigned long long h_stats[2];
     memcpy(h_stats, h_small + 8, sizeof(h_stats));
     if (c_size > 0x7FFFFFFFll || h_stats[1] > 0xFFFFFFFFull) {
@@ -1060,6 +1087,8 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
             SG_CUDA(cudaEventSynchronize(ev[2]));
             cudaEventElapsedTime(&info->symbolic_ms, ev[0], ev[1]);
             cudaEventElapsedTime(&info->numeric_ms, ev[1], ev[2]);
+            cudaEventElapsedTime(&info->count_ms, ev[0], ev[3]);
+            cudaEventElapsedTime(&info->fill_ms, ev[3], ev[1]);
             info->total_ms = info->symbolic_ms + info->numeric_ms;
         }
     }

@@ -516,13 +516,23 @@ __global__ void halo_flag_kernel(const HaloDev h) {
         for (int p = 0; p < h.n_peer; p++) st_release_sys(h.peer_flag[p], h.signal_epoch);
     }
 }
-// stand-alone push (first exchange after set_x, and products that run the block-parallel kernel)
-__global__ void __launch_bounds__(256) halo_push_kernel(const float* __restrict__ y, const HaloDev h) {
-    for (int i = 0; i < h.n_push; i++) {
-        const int n = h.hi[i] - h.lo[i];
-        const float* src = y + h.lo[i];
-        float* d = h.dst[i];
-        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) d[k] = src[k];
+// stand-alone push (first exchange after set_x, and products that run the block-parallel kernel): every thread reads four rows of y
+// once and stores them to every peer range that contains them -- 16-byte stores, 512 contiguous bytes per warp and peer, all
+// peers' links busy at the same time (for a scattered matrix every peer needs the whole slice: an all-gather written by the owner)
+__global__ void __launch_bounds__(256) halo_push_kernel(const float* __restrict__ y, int rows, const HaloDev h) {
+    int lo_all = 0x7FFFFFFF, hi_all = 0;
+    for (int i = 0; i < h.n_push; i++) { lo_all = min(lo_all, h.lo[i]); hi_all = max(hi_all, h.hi[i]); }
+    for (int r = lo_all + 4 * (int)(blockIdx.x * blockDim.x + threadIdx.x); r < hi_all; r += 4 * (int)(gridDim.x * blockDim.x)) {
+        float v[4];
+        if (r + 4 <= rows) { const float4 t = *reinterpret_cast<const float4*>(y + r); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+        else { for (int q = 0; q < 4; q++) v[q] = r + q < rows ? y[r + q] : 0.f; }
+        for (int i = 0; i < h.n_push; i++) {
+            const int lo = h.lo[i], hi = h.hi[i];
+            if (r >= hi || r + 4 <= lo) continue;
+            float* d = h.dst[i] + (r - lo);
+            if (r >= lo && r + 4 <= hi) *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+            else { for (int q = 0; q < 4; q++) if (r + q >= lo && r + q < hi) d[q] = v[q]; }
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -720,9 +730,29 @@ __device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volat
 
 constexpr int STREAM_DR = 8, STREAM_PD = 4;      // descriptor ring slots / prefetch distance of a producer
 
+// Multi-GPU code of the streaming kernel, kept out of line: inlined, it cost the multiply loop its register allocation (ncu, one
+// GPU acting as its own peer: 64.5 M warp instructions against 51.9 M, 82 us against 68 us) although it runs for 16 tiles of 32768.
+__device__ __noinline__ bool halo_tile_pushes(const HaloDev* hd, int t, int trow0, int trow1) {
+    bool part = t == hd->solo_tile;
+    for (int i = 0; i < hd->n_push; i++) part |= hd->lo[i] < trow1 && hd->hi[i] > trow0;
+    return part;
+}
+__device__ __noinline__ bool halo_tile_waits(const HaloDev* hd, int t, int trow0, int trow1, int nb, int lmin, int lmax) {
+    return halo_tile_pushes(hd, t, trow0, trow1) || (nb > 0 && ((int64_t)lmin * 32 < hd->own_c0 || ((int64_t)lmax + 1) * 32 > hd->own_c1));
+}
+__device__ __noinline__ void halo_wait_all(const HaloDev* hd, int lane) {
+    if (lane < hd->n_peer) halo_wait(*hd, lane);
+}
+__device__ __noinline__ void halo_push_tile(const HaloDev* hd, int row, int rows, bool active, float a0, float a1, float a2, float a3, int gt, int bar_id, int nthreads) {
+    if (active) { const float acc[4] = {a0, a1, a2, a3}; halo_store<4>(*hd, row, rows, acc); }
+    __threadfence_system();
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+    if (gt == 0) halo_signal(*hd);
+}
+
 template <typename T, typename X, int RTT, int NG, int MINB, typename H = NoHalo>
-__global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(const StreamArgs<T> sa, const X* __restrict__ x, float* __restrict__ y,
-                                                                               const H hd) {
+__global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(const __grid_constant__ StreamArgs<T> sa, const X* __restrict__ x,
+                                                                               float* __restrict__ y, const __grid_constant__ H hd) {
     constexpr bool DIST = !std::is_same<H, NoHalo>::value;
     constexpr int GT = RTT * 2;            // consumer threads of a group: two per block row
     constexpr int VA = 16 / sizeof(T);
@@ -822,11 +852,8 @@ __global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(
                 // A tile whose x lines leave this rank's own columns must not read x before the peers' rows are in, and a tile that
                 // pushes rows waits too (back-pressure, see spmv_tile_kernel).  The producer waits on the tile's behalf before it
                 // completes `full`; the rotated tile order puts these tiles mid-kernel, where the wait is over before it starts.
-                const int trow0 = r0 * 8, trow1 = min(a.rows, (r0 + nrow) * 8);
-                bool part = t == hd.solo_tile;
-                for (int i = 0; i < hd.n_push; i++) part |= hd.lo[i] < trow1 && hd.hi[i] > trow0;
-                if (part || (nb > 0 && ((int64_t)d1.z * 32 < hd.own_c0 || ((int64_t)d1.w + 1) * 32 > hd.own_c1))) {
-                    if (lane < hd.n_peer) halo_wait(hd, lane);
+                if (halo_tile_waits(&hd, t, r0 * 8, min(a.rows, (r0 + nrow) * 8), nb, d1.z, d1.w)) {
+                    halo_wait_all(&hd, lane);
                     __syncwarp();
                 }
             }
@@ -897,15 +924,8 @@ __global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(
                 }
             }
             if constexpr (DIST) {
-                const int trow0 = r0 * 8, trow1 = min(a.rows, (r0 + nrow) * 8);
-                bool part = t == hd.solo_tile;
-                for (int i = 0; i < hd.n_push; i++) part |= hd.lo[i] < trow1 && hd.hi[i] > trow0;
-                if (part) {
-                    if (active) halo_store<4>(hd, row, a.rows, acc);
-                    __threadfence_system();
-                    bar_sync_named(1 + g, GT);
-                    if (gt == 0) halo_signal(hd);
-                }
+                if (halo_tile_pushes(&hd, t, r0 * 8, min(a.rows, (r0 + nrow) * 8)))
+                    halo_push_tile(&hd, row, a.rows, active, acc[0], acc[1], acc[2], acc[3], gt, 1 + g, GT);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + s);
@@ -920,18 +940,18 @@ __global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(
 // warp scans of popc (value offsets) interleave, and the first value / x element of each of the UNR blocks -- with
 // about one value per block that is nearly all of them -- are loaded back to back before any of them is used, so a
 // step has 4 * UNR independent loads in flight per lane instead of a chain of four dependent ones.
-// H = HaloDev: the multi-GPU variant -- every finished row is stored to the peers that need it (for a scattered matrix: all of
-// them -- an all-gather written by the producers, spread over the whole kernel instead of a copy pass after it).  The wait
-// for the peers' epoch and the publication of this one are one-thread kernels around the product, not per-CTA code: a system
-// fence invalidates the SM's whole L1 (SASS: MEMBAR.SYS + CCTL.IVALL), and this kernel lives on L1 hits of its x gathers --
-// with a fence at the start and the end of every CTA the 2-GPU R-MAT-22 product took 1161 us against 600 us on one GPU.
-template <typename T, typename X, typename H = NoHalo>
+// Multi-GPU: the product itself is unchanged; a wait kernel before it and halo_push_kernel after it do the exchange (bmsp_spmv_halo).
+// Two in-kernel variants were measured and dropped.  Every warp storing its finished block row to the peers (32-byte pieces):
+// 3.78x at 8 GPUs on R-MAT-22 -- NVLink wants 256-byte writes.  Collecting a CTA's eight block rows in shared memory and storing
+// 256 bytes per peer: the CTA-wide barrier keeps seven warps waiting for the one that drew a hub-row slice (2 GPUs: 404 us against
+// 368 us).  And a system fence per CTA invalidates the SM's L1 (SASS: MEMBAR.SYS + CCTL.IVALL), which this kernel lives on: with
+// fences at the start and the end of every CTA the 2-GPU product took 1161 us against 600 us on one GPU.
+template <typename T, typename X>
 __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __restrict__ bmps, const int32_t* __restrict__ bcol,
                                                            const uint64_t* __restrict__ offsets, const T* __restrict__ values,
                                                            const int4* __restrict__ work, int n_work, int rows,
                                                            const X* __restrict__ x, float* __restrict__ y,
-                                                           float* __restrict__ partial, const H hd) {
-    constexpr bool DIST = !std::is_same<H, NoHalo>::value;
+                                                           float* __restrict__ partial) {
     constexpr int UNR = 4;
     __shared__ float s_acc[8][8][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1003,13 +1023,7 @@ __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __re
         if (w.w) partial[(int64_t)item * 8 + lane] = res;
         else {
             const int64_t row = (int64_t)w.x * 8 + lane;
-            if (row < rows) {
-                y[row] = res;
-                if constexpr (DIST) {
-                    for (int i = 0; i < hd.n_push; i++)
-                        if (row >= hd.lo[i] && row < hd.hi[i]) hd.dst[i][row - hd.lo[i]] = res;
-                }
-            }
+            if (row < rows) y[row] = res;
         }
     }
 }
@@ -1020,10 +1034,8 @@ __global__ void split_list_kernel(const int32_t* __restrict__ item_ofs, int nbr,
     if (br < nbr && item_ofs[br + 1] - item_ofs[br] > 1) list[atomicAdd(count, 1)] = br;
 }
 
-template <typename H = NoHalo>
 __global__ void spmv_fixup_kernel(const int32_t* __restrict__ item_ofs, const float* __restrict__ partial, const int32_t* __restrict__ split_list,
-                                  int n_split_rows, int rows, float* __restrict__ y, const H hd) {
-    constexpr bool DIST = !std::is_same<H, NoHalo>::value;     // multi-GPU variant: the finished rows also go to the peers
+                                  int n_split_rows, int rows, float* __restrict__ y) {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     if ((gt >> 3) < n_split_rows) {
         const int br = split_list[gt >> 3], r = gt & 7;
@@ -1033,10 +1045,6 @@ __global__ void spmv_fixup_kernel(const int32_t* __restrict__ item_ofs, const fl
             float s = 0.f;
             for (int i = i0; i < i1; i++) s += partial[(int64_t)i * 8 + r];
             y[row] = s;
-            if constexpr (DIST) {
-                for (int i = 0; i < hd.n_push; i++)
-                    if (row >= hd.lo[i] && row < hd.hi[i]) hd.dst[i][row - hd.lo[i]] = s;
-            }
         }
     }
 }
@@ -1232,16 +1240,13 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, 
         return launch_tile_kernel<T, X, 64, 2, 12, H>(a, x, y, hd, grid, smem, st);
     }
     const unsigned grid1 = (unsigned)ceil_div(A->n_work, 8), grid2 = (unsigned)ceil_div((int64_t)A->n_split_rows * 8, 256);
-    constexpr bool DIST = !std::is_same<H, NoHalo>::value;
-    if constexpr (DIST) { halo_wait_kernel<<<1, 32, 0, st>>>(hd); BMSP_KERNEL_CHECK(); }
-    spmv_blockpar_kernel<T, X, H><<<grid1, 256, 0, st>>>(A->bmps, A->bcol, A->offsets, (const T*)A->values, (const int4*)A->work, A->n_work,
-                                                       A->rows, x, y, A->split_partial, hd);
+    spmv_blockpar_kernel<T, X><<<grid1, 256, 0, st>>>(A->bmps, A->bcol, A->offsets, (const T*)A->values, (const int4*)A->work, A->n_work,
+                                                    A->rows, x, y, A->split_partial);
     BMSP_KERNEL_CHECK();
     if (A->n_split > 0) {
-        spmv_fixup_kernel<H><<<grid2, 256, 0, st>>>(A->split_rows, A->split_partial, A->split_list, A->n_split_rows, A->rows, y, hd);
+        spmv_fixup_kernel<<<grid2, 256, 0, st>>>(A->split_rows, A->split_partial, A->split_list, A->n_split_rows, A->rows, y);
         BMSP_KERNEL_CHECK();
     }
-    if constexpr (DIST) { halo_flag_kernel<<<1, 32, 0, st>>>(hd); BMSP_KERNEL_CHECK(); }
     return BMSP_OK;
 }
 
@@ -1463,9 +1468,12 @@ extern "C" int bmsp_halo_push(const float* y_own, int32_t rows, const bmsp_halo_
     if (h.n_peer == 0) return BMSP_OK;
     int64_t total = 0;
     for (int i = 0; i < h.n_push; i++) total += h.hi[i] - h.lo[i];
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 1024), 592));
+    int lo_all = 0x7FFFFFFF, hi_all = 0;
+    for (int i = 0; i < h.n_push; i++) { lo_all = std::min(lo_all, h.lo[i]); hi_all = std::max(hi_all, h.hi[i]); }
+    (void)total;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div((int64_t)std::max(0, hi_all - lo_all), 1024), 592));
     h.signal_epoch = signal_epoch; h.n_sig = (uint32_t)grid;
-    halo_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y_own, h);
+    halo_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y_own, rows, h);
     BMSP_KERNEL_CHECK();
     return BMSP_OK;
 }
@@ -1511,10 +1519,7 @@ extern "C" int bmsp_spmv_halo(bmsp_matrix_t A, const float* x_ext, float* y_own,
         return A->dtype == BMSP_F16 ? launch_spmv<__half, float, HaloDev>(A, x_ext, y_own, st, 0, -1, h)
                                     : launch_spmv<float, float, HaloDev>(A, x_ext, y_own, st, 0, -1, h);
     }
-    if (A->spmv_path == 1 && fused)
-        return A->dtype == BMSP_F16 ? launch_spmv<__half, float, HaloDev>(A, x_ext, y_own, st, 0, -1, h)
-                                    : launch_spmv<float, float, HaloDev>(A, x_ext, y_own, st, 0, -1, h);
-    // BMSP_HALO_FUSED=0: wait kernel, product, push kernel
+    // block-parallel path (and BMSP_HALO_FUSED=0): wait kernel, product, push kernel
     halo_wait_kernel<<<1, 32, 0, st>>>(h);
     BMSP_KERNEL_CHECK();
     BMSP_TRY(bmsp_spmv(A, x_ext, BMSP_F32, y_own, stream));

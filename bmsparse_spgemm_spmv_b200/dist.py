@@ -190,6 +190,7 @@ class PeerHalo:
         from .matrix import _alias
         self = cls()
         self.epoch = 0
+        self._args = {}
         self.opened = {}
         self.base = None
         ok = True
@@ -237,11 +238,18 @@ class PeerHalo:
         L.check(L.lib().bmsp_halo_push(C.c_void_p(own.data_ptr()), own.numel(), C.byref(self.desc[sh.cur]), C.c_uint32(self.epoch), _stream_ptr()))
 
     def step(self, sh, nxt):
-        import ctypes as C
-        from . import _lib as L
-        from .matrix import _stream_ptr
-        L.check(L.lib().bmsp_spmv_halo(sh.local._h, C.c_void_p(self.x[sh.cur].data_ptr()), C.c_void_p(sh.own_slice(self.x[nxt]).data_ptr()),
-                                       C.byref(self.desc[nxt]), C.c_uint32(self.epoch), C.c_uint32(self.epoch + 1), _stream_ptr()))
+        """one fused product.  The call's arguments only depend on which of the three buffers is current: they are built once per
+        buffer (a 68 us kernel leaves no room for ~40 us of per-step Python: tensor slicing, data_ptr(), byref)."""
+        args = self._args.get(sh.cur)
+        if args is None:
+            import ctypes as C
+            from . import _lib as L
+            from .matrix import _stream_ptr
+            args = (L.lib().bmsp_spmv_halo, sh.local._h, C.c_void_p(self.x[sh.cur].data_ptr()), C.c_void_p(sh.own_slice(self.x[nxt]).data_ptr()),
+                    C.byref(self.desc[nxt]), _stream_ptr(), L.check)
+            self._args[sh.cur] = args
+        fn, h, xp, yp, dref, st, check = args
+        check(fn(h, xp, yp, dref, self.epoch, self.epoch + 1, st))
         self.epoch += 1
 
     def check(self):

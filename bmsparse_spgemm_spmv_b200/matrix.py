@@ -36,10 +36,11 @@ def _alias(ptr, n, typestr, torch_dtype, owner):
 
 
 class bmSpMatrix:
-    def __init__(self, path: str | None = None, transpose: bool = False, dtype=torch.float16, _handle=None):
+    def __init__(self, path: str | None = None, transpose: bool = False, dtype=torch.float16, _handle=None, merge_duplicates: bool = False):
         self._h = C.c_void_p(_handle) if _handle else C.c_void_p()
         if path is not None:
-            L.check(L.lib().bmsp_create_from_mtx(path.encode(), int(transpose), _dt(dtype), _stream_ptr(), C.byref(self._h)))
+            L.check(L.lib().bmsp_create_from_mtx_ex(path.encode(), int(transpose), _dt(dtype), int(bool(merge_duplicates)), _stream_ptr(),
+                                                    C.byref(self._h)))
 
     # ---- constructors -------------------------------------------------------------------------
     @classmethod
@@ -67,13 +68,13 @@ class bmSpMatrix:
         return m
 
     @classmethod
-    def from_coo(cls, num_rows, num_cols, rows, cols, vals, transpose=False, dtype=torch.float16):
+    def from_coo(cls, num_rows, num_cols, rows, cols, vals, transpose=False, dtype=torch.float16, merge_duplicates=False):
         m = cls()
         r = np.ascontiguousarray(rows, np.int32); c = np.ascontiguousarray(cols, np.int32)
         v = np.ascontiguousarray(vals, np.float64)
-        L.check(L.lib().bmsp_create_from_coo(int(num_rows), int(num_cols), C.c_int64(r.size), r.ctypes.data_as(C.c_void_p),
-                                             c.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), int(transpose),
-                                             _dt(dtype), _stream_ptr(), C.byref(m._h)))
+        L.check(L.lib().bmsp_create_from_coo_ex(int(num_rows), int(num_cols), C.c_int64(r.size), r.ctypes.data_as(C.c_void_p),
+                                                c.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), int(transpose),
+                                                _dt(dtype), int(bool(merge_duplicates)), _stream_ptr(), C.byref(m._h)))
         return m
 
     @classmethod
@@ -166,6 +167,22 @@ class bmSpMatrix:
         a = C.c_int64(); b = C.c_int64(); mean = C.c_double(); mx = C.c_double()
         p = lambda x: x.ctypes.data_as(C.c_void_p)
         L.check(L.lib().bmsp_compare(self._h, C.c_int64(r.size), p(r), p(c), p(v), C.byref(a), C.byref(b), C.byref(mean), C.byref(mx)))
+        return a.value, b.value, mean.value, mx.value
+
+    def to_csr(self):
+        """bmSparse -> CSR on the device: (row_ptr int32[rows+1], col_idx int32[nnz], vals fp32[nnz]) as CUDA tensors."""
+        v = self._view()
+        rp = torch.empty(v.num_rows + 1, dtype=torch.int32, device="cuda"); ci = torch.empty(max(v.nnz, 1), dtype=torch.int32, device="cuda")
+        vals = torch.empty(max(v.nnz, 1), dtype=torch.float32, device="cuda")
+        L.check(L.lib().bmsp_to_csr(self._h, C.c_void_p(rp.data_ptr()), C.c_void_p(ci.data_ptr()), C.c_void_p(vals.data_ptr()), L.DEVICE, _stream_ptr()))
+        return rp, ci[:v.nnz], vals[:v.nnz]
+
+    def compare_csr(self, row_ptr, col_idx, vals):
+        """device-side compare against a CSR held in CUDA tensors: (only_in_self, only_in_other, mean_rel, max_rel)"""
+        rp = row_ptr.to(torch.int32).contiguous(); ci = col_idx.to(torch.int32).contiguous(); v = vals.to(torch.float32).contiguous()
+        a = C.c_int64(); b = C.c_int64(); mean = C.c_double(); mx = C.c_double()
+        L.check(L.lib().bmsp_compare_csr(self._h, C.c_void_p(rp.data_ptr()), C.c_void_p(ci.data_ptr()), C.c_void_p(v.data_ptr()), L.DEVICE,
+                                         _stream_ptr(), C.byref(a), C.byref(b), C.byref(mean), C.byref(mx)))
         return a.value, b.value, mean.value, mx.value
 
     def block_transpose(self, dtype=None):

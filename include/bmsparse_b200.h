@@ -73,6 +73,8 @@ typedef struct {          /* per-phase device times of the last bmsp_spgemm (CUD
     float total_ms;
     int64_t candidate_pairs, surviving_pairs, c_blocks, c_nnz;
     int32_t numeric_path; /* 0 scalar, 1 mma.sync                                                   */
+    float count_ms;       /* symbolic, first pass: block-row spans, candidate pairs, filter, C blocks per row (T_1..T_4) */
+    float fill_ms;        /* symbolic, second pass: pair list, keys in order, bitmaps, offsets (T_5, T_6, T_9)           */
 } bmsp_spgemm_info;
 
 typedef struct {
@@ -111,6 +113,16 @@ int bmsp_create_from_coo(int32_t rows, int32_t cols, int64_t nnz, const int32_t*
 int bmsp_create_from_mtx(const char* path, int32_t transposed, int32_t out_dtype, void* stream,
                          bmsp_matrix_t* out);
 
+/* The same two with a flags word: BMSP_MERGE_DUPLICATES sums repeated (row, col) entries instead of rejecting them
+ * (BMSP_ERR_DUPLICATE).  MatrixMarket banners: real / integer / pattern, general / symmetric / skew-symmetric (mirror negated);
+ * complex, hermitian and array storage return BMSP_ERR_UNSUPPORTED (cusp/io/detail/matrix_market.inl:155-330 is the spec). */
+#define BMSP_MERGE_DUPLICATES 1
+int bmsp_create_from_coo_ex(int32_t rows, int32_t cols, int64_t nnz, const int32_t* row_idx,
+                            const int32_t* col_idx, const double* vals, int32_t transposed,
+                            int32_t out_dtype, int32_t flags, void* stream, bmsp_matrix_t* out);
+int bmsp_create_from_mtx_ex(const char* path, int32_t transposed, int32_t out_dtype, int32_t flags, void* stream,
+                            bmsp_matrix_t* out);
+
 /* Adopt existing bmSparse arrays (copied).  Replaces the swap-in constructor bmSpMatrix.cu:30-43.
  * offsets_len is block_num or block_num+1. */
 int bmsp_create_from_arrays(int32_t rows, int32_t cols, int64_t block_num, int64_t nnz,
@@ -133,6 +145,16 @@ int bmsp_to_coo(bmsp_matrix_t m, int32_t* rows, int32_t* cols, float* vals);
 int bmsp_compare(bmsp_matrix_t m, int64_t nnz, const int32_t* rows, const int32_t* cols,
                  const float* vals, int64_t* only_in_m, int64_t* only_in_coo, double* mean_rel_err,
                  double* max_rel_err);
+
+/* bmSparse -> CSR on the device (row-major decode: the blocks of a block row are already in column order, so no sort): row_ptr
+ * int32[num_rows + 1], col_idx int32[nnz] ascending inside each row, vals fp32[nnz].  `mem` says where the three output arrays
+ * live (BMSP_DEVICE: written in place, asynchronous on `stream`; BMSP_HOST: copied out, synchronous).  This is the export the
+ * reference's CSRMatrix class was declared for (include/CSRMatrix.h:15-17) and what feeds cuSPARSE / cusp consumers. */
+int bmsp_to_csr(bmsp_matrix_t m, int32_t* row_ptr, int32_t* col_idx, float* vals, int32_t mem, void* stream);
+/* bmsp_compare against a CSR (columns ascending inside each row), on the device: both sides are in key order, so one thread
+ * per row merges the two column lists -- nothing is sorted and nothing but four numbers comes back to the host. */
+int bmsp_compare_csr(bmsp_matrix_t m, const int32_t* row_ptr, const int32_t* col_idx, const float* vals, int32_t mem,
+                     void* stream, int64_t* only_in_m, int64_t* only_in_csr, double* mean_rel_err, double* max_rel_err);
 
 /* ---- operators ----------------------------------------------------------------------------- */
 /* y = A x.  Replaces bmSparse_SpMV<ValueIn,ValueOut>(A, v, u, batched) (SPMV.cu:191-230).

@@ -57,3 +57,15 @@ def test_cpp_shim_headers_compile(tmp_path):
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_reference_mains_compile_against_the_shim():
+    """build() compiles the reference's main() bodies unchanged against include/ whenever the reference tree is present; the
+    binaries must exist then (they are run on the GPU box by tests/test_gpu_cpp_shim.py)."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir("/root/reference/src"):
+        import pytest
+        pytest.skip("reference tree absent")
+    for name in ("ref_main_spgemm", "ref_main_spmv", "thrust_shim"):
+        assert os.path.exists(os.path.join(root, "tools", "_build", name)), f"{name}: run __graft_entry__.build()"

@@ -149,3 +149,115 @@ def test_device_csr_row_ptr_is_validated(B):
         with pytest.raises(L.BmspError) as e:
             B.bmSpMatrix.from_csr(nr, nc, bad, ci, v)
         assert e.value.code == 1
+
+
+def _write(path, banner, size, lines):
+    with open(path, "w") as f:
+        f.write(banner + "\n% a comment\n" + size + "\n" + "\n".join(lines) + "\n")
+
+
+def test_matrix_market_banners(B, tmp_path):
+    """MatrixMarket parity (cusp/io/detail/matrix_market.inl:155-330 is the behavioural spec): pattern / integer / real, general /
+    symmetric / skew-symmetric against scipy.io.mmread; complex, hermitian and array storage are refused; indices are range-checked;
+    duplicates are rejected unless merging is asked for."""
+    import scipy.io
+    import scipy.sparse as sp
+    import bmsparse_spgemm_spmv_b200._lib as L
+    rng = np.random.default_rng(5)
+    n = 37
+    ent = sorted({(int(r), int(c)) for r, c in zip(rng.integers(0, n, 300), rng.integers(0, n, 300)) if r > c})     # strictly lower triangle
+    diag = [(i, i) for i in range(0, n, 3)]
+    cases = {
+        "real general": ([(r, c) for r, c in ent] + [(c, r) for r, c in ent[:40]] + diag, False),
+        "integer symmetric": (ent + diag, False),
+        "real skew-symmetric": (ent, False),
+        "pattern symmetric": (ent + diag, True),
+        "pattern general": (ent, True),
+    }
+    for kind, (entries, pattern) in cases.items():
+        path = str(tmp_path / (kind.replace(" ", "_") + ".mtx"))
+        typ = kind.split()[0]
+        lines = []
+        for k, (r, c) in enumerate(entries):
+            val = "" if pattern else (f" {(k % 7) - 3 or 2}" if typ == "integer" else f" {((k * 37) % 17 - 8) / 4.0 or 0.5}")
+            lines.append(f"{r + 1} {c + 1}{val}")
+        _write(path, f"%%MatrixMarket matrix coordinate {kind}", f"{n} {n} {len(entries)}", lines)
+        ref = sp.coo_matrix(scipy.io.mmread(path)).tocsr()
+        ref.sort_indices()
+        M = B.bmSpMatrix(path, False, dtype=torch.float32)
+        rp, ci, v = M.to_csr()
+        assert np.array_equal(rp.cpu().numpy(), ref.indptr) and np.array_equal(ci.cpu().numpy(), ref.indices), kind
+        assert np.array_equal(v.cpu().numpy(), ref.data.astype(np.float32)), kind
+        # the device-side compare agrees: nothing missing on either side, zero error
+        assert M.compare_csr(torch.from_numpy(ref.indptr).cuda(), torch.from_numpy(ref.indices).cuda(), torch.from_numpy(ref.data.astype(np.float32)).cuda()) == (0, 0, 0.0, 0.0)
+    for banner in ("coordinate complex general", "coordinate real hermitian", "array real general"):
+        path = str(tmp_path / "bad.mtx")
+        _write(path, f"%%MatrixMarket matrix {banner}", "3 3 1", ["1 1 1.0 0.0"])
+        with pytest.raises(L.BmspError) as e:
+            B.bmSpMatrix(path, False)
+        assert e.value.code == 7, banner                                        # BMSP_ERR_UNSUPPORTED
+    path = str(tmp_path / "range.mtx")
+    _write(path, "%%MatrixMarket matrix coordinate real general", "3 3 2", ["1 1 1.0", "4 2 1.0"])
+    with pytest.raises(L.BmspError) as e:
+        B.bmSpMatrix(path, False)
+    assert e.value.code == 8                                                    # BMSP_ERR_RANGE
+    path = str(tmp_path / "short.mtx")
+    _write(path, "%%MatrixMarket matrix coordinate real general", "3 3 3", ["1 1 1.0", "2 2 1.0"])
+    with pytest.raises(L.BmspError) as e:
+        B.bmSpMatrix(path, False)
+    assert e.value.code == 5                                                    # BMSP_ERR_IO
+    path = str(tmp_path / "dup.mtx")
+    _write(path, "%%MatrixMarket matrix coordinate real general", "9 9 4", ["1 1 1.5", "2 3 2.0", "1 1 0.25", "2 3 -2.0"])
+    with pytest.raises(L.BmspError) as e:
+        B.bmSpMatrix(path, False)
+    assert e.value.code == 4                                                    # BMSP_ERR_DUPLICATE
+    M = B.bmSpMatrix(path, False, dtype=torch.float32, merge_duplicates=True)
+    rp, ci, v = M.to_csr()
+    assert rp.cpu().tolist()[:3] == [0, 1, 2] and ci.cpu().tolist() == [0, 2] and v.cpu().tolist() == [1.75, 0.0]
+
+
+def test_large_mtx_is_parsed_in_parallel(B, oracle, tmp_path):
+    """a file above the one-thread threshold (1 MB): the sliced parse must give the same matrix as the oracle's conversion"""
+    rp, ci, v = random_csr(3000, 3000, 0.02, seed=11)
+    rows = csr_rows(rp)
+    path = str(tmp_path / "big.mtx")
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n")
+        f.write(f"3000 3000 {ci.size}\n")
+        f.write("".join(f"{r + 1} {c + 1} {float(x)!r}\n" for r, c, x in zip(rows.tolist(), ci.tolist(), v.tolist())))
+    assert os.path.getsize(path) > (1 << 20)
+    M = B.bmSpMatrix(path, False)
+    exp = oracle.csr_to_bmsp(3000, 3000, rp, ci, v)
+    k, b, o, vals = M.download()
+    assert_structure_equal((k, b, o), exp, "big.mtx")
+    assert np.array_equal(vals.astype(np.float32), exp.values)
+
+
+@pytest.mark.parametrize("gen", ["poisson", "random", "rmat", "clustered"])
+def test_to_csr_and_device_compare(B, gen):
+    """bmSparse -> CSR on the device gives back the CSR the matrix was built from (fp16-rounded values), and the device-side
+    compare reports real numbers: missing entries on either side and the relative error of a perturbed copy"""
+    G = B.generators
+    if gen == "poisson": nr, nc, rp, ci, v = G.poisson5pt(70, 53)
+    elif gen == "rmat": nr, nc, rp, ci, v = G.rmat(12)
+    elif gen == "clustered": nr, nc, rp, ci, v = G.block_clustered(200)
+    else:
+        nr, nc = 1001, 777
+        rp, ci, v = random_csr(nr, nc, 0.03, seed=3, empty_block_rows=(1, 5))
+    M = B.bmSpMatrix.from_csr(nr, nc, rp, ci, v)
+    rp2, ci2, v2 = M.to_csr()
+    assert np.array_equal(rp2.cpu().numpy(), rp) and np.array_equal(ci2.cpu().numpy(), ci)
+    assert np.array_equal(v2.cpu().numpy(), v.astype(np.float16).astype(np.float32))
+    assert M.compare_csr(rp2, ci2, v2) == (0, 0, 0.0, 0.0)
+    # drop two entries of the other side, perturb one value
+    keep = np.ones(ci.size, bool); keep[[3, ci.size // 2]] = False
+    rows = csr_rows(rp)
+    rp3 = np.zeros(nr + 1, np.int64); np.cumsum(np.bincount(rows[keep], minlength=nr), out=rp3[1:])
+    v3 = v2.cpu().numpy()[keep].copy(); v3[10] *= 1.5
+    a, b, mean, mx = M.compare_csr(torch.from_numpy(rp3.astype(np.int32)).cuda(), torch.from_numpy(ci[keep]).cuda(), torch.from_numpy(v3).cuda())
+    assert (a, b) == (2, 0) and abs(mx - 1.0 / 3.0) < 1e-6 and abs(mean - (1.0 / 3.0) / (ci.size - 2)) < 1e-9
+    # the host-COO entry point (any order) goes through the same device comparison
+    perm = np.random.default_rng(0).permutation(ci.size)
+    assert M.compare(rows[perm], ci[perm], v2.cpu().numpy()[perm]) == (0, 0, 0.0, 0.0)
+    with pytest.raises(Exception):
+        B.bmSpMatrix.from_csr(nr, nc, rp, ci, v, transpose=True).to_csr()
