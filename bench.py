@@ -115,6 +115,33 @@ class ClockSampler(threading.Thread):
                 "samples": len(inside), "where": where}
 
 
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers of the e2e leg are allocated
+    (first touch places their pages on that node): at N > 1 every rank pushes 134 MB per step through host memory, and buffers on
+    the far socket were part of why the round-1 e2e step grew 4.6x from N = 1 to N = 8.  Best effort; returns what it did."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return {"node": node, "bound": False}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"bound": False, "why": str(e)[:80]}
+
+
 # ------------------------------------------------------------------------------------------------ CPU baseline / reference arm
 def cpu_spmv_baseline(O, nr, nc, rp, ci, v, x, nbytes, reps, slabs=1):
     """reference cusp host CSR SpMV (sequential = thrust::cpp dispatch, and the OMP back-end) on this box's host cores.
@@ -444,6 +471,7 @@ def main():
 
     # ---- end to end through the public API with HOST buffers: H2D x, SpMV, D2H y inside the timed region
     ncols_local = nc if world == 1 else A.num_cols
+    numa = bind_to_gpu_numa(local) if world > 1 else {"bound": False, "why": "single rank: left to the scheduler"}
     xp = torch.zeros(ncols_local, dtype=torch.float32).pin_memory()
     xoff = 0 if world == 1 else sharded.own_lo - sharded.ext_lo
     xp[xoff:xoff + nr].copy_(torch.from_numpy(x_host))
@@ -488,7 +516,7 @@ def main():
                      "frac_of_nominal_8TBs": nbytes / (kern_ms * 1e-3) / 1e9 / 8000.0,
                      "kernel": kname, "kernel_ms": kern_ms},
         "e2e": {"value": total_bytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": ncols_local * 4, "d2h_bytes_per_step": nr * 4,
-                "ms_per_step": e2e_s * 1e3, "note": "bmsp_spmv_host: matrix resident in HBM (as in the reference's timed region); every step x comes from pinned host memory in chunks on a copy stream while the row-range launches of the same kernel store y straight into the pinned host buffer (PCIe-bound both ways)"},
+                "ms_per_step": e2e_s * 1e3, "numa": numa, "note": "bmsp_spmv_host: matrix resident in HBM (as in the reference's timed region); every step x comes from pinned host memory in chunks on a copy stream while the row-range launches of the same kernel store y straight into the pinned host buffer (PCIe-bound both ways)"},
         "gpu_launches": K * launches_per_step,
         "clocks": clocks,
     }

@@ -27,6 +27,13 @@ struct bmsp_matrix_s {
     uint32_t* rvb = nullptr;    // [nbr+1] first value index of each block row
     uint8_t* kmask = nullptr;   // [nblk]  OR of the 8 bitmap bytes: inner-dimension (k) occupancy
     void* pmeta = nullptr;      // [nblk]  uint4 {bitmap lo, hi, block column, value offset}; built by the first SpGEMM that uses this matrix as B
+    // SpGEMM, sparse-block operands: B's blocks bucketed by inner index (block row k, bit t of kmask) -- spgemm.cu, "fine index"
+    int32_t fine_state = 0;     // 0 not examined yet, 1 built, -1 not worth it (dense blocks: the buckets would replicate every block ~8 times)
+    uint32_t* fine_ptr = nullptr;   // [nbr * 8 + 1] bucket offsets
+    uint32_t* fine_bcol = nullptr;  // [fine_n] block column of the bucket entry
+    uint8_t* fine_kmask = nullptr;  // [fine_n] kmask of the bucket entry's block (de-duplicates blocks that sit in several buckets)
+    void* fine_rec = nullptr;       // [fine_n] 32-byte records {bitmap lo, hi, block column, value offset}, {first 8 values}
+    int64_t fine_n = 0;
     // SpMV plan (spmv.cu)
     int32_t spmv_path = -2;     // -2 not planned yet, 0 row-tiled (dense-ish blocks), 1 block-parallel (sparse blocks)
     int32_t cap_blk = 0, cap_val = 0;   // per-tile smem capacities of the row-tiled kernels
@@ -46,6 +53,13 @@ struct bmsp_matrix_s {
     int32_t n_split_rows = 0;
     int32_t max_row_blocks = 0;
     void* host_pipe = nullptr;  // HostPipe (spmv.cu): streams, events and staging buffers of bmsp_spmv_host
+    // multi-GPU product (spmv.cu, bmsp_spmv_halo): the tiles that depend on the peers or push rows to them ("boundary"), and the rest
+    int32_t* halo_tiles = nullptr;      // [ntiles] boundary tiles first (ascending), then the interior tiles (ascending)
+    int32_t halo_n_boundary = -1;       // -1: not classified yet
+    int32_t halo_first = 0;             // the first boundary tile
+    cudaStream_t halo_side = nullptr;   // the boundary launch runs here, next to the interior launch on the caller's stream
+    cudaEvent_t halo_fork = nullptr, halo_join = nullptr;
+    int32_t halo_key[2 + 16] = {0};     // own column range + push ranges the lists were built for
     // Stream ordering of the handle's memory: every entry point that enqueues work on the arrays records its stream here
     // (bmsp::touch).  bmsp_destroy frees on that stream, so the frees are ordered behind the kernels that still read or write the
     // arrays; a handle that was used on more than one stream is drained with a device synchronisation first.  Streams passed to

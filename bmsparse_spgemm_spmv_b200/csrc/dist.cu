@@ -11,8 +11,9 @@ namespace bmsp {
 
 // SpMV cost of a block row in byte units: its blocks and values, plus a per-row term.  The row-tiled kernel pays little per row
 // (row pointers, y); the block-parallel kernel spends a whole warp on every block row, worth about 20 blocks of streaming
-// (fitted on the R-MAT-22 shards of a 2-GPU run, round 2: 7.9 us per 10^6 blocks + 41 us per 10^6 matrix rows, i.e. a block row
-// costs as much as ~600 bytes of streaming).
+// (fitted on the R-MAT-22 shards of a 2-GPU run, round 2: 7.9 us per 10^6 blocks + 41 us per 10^6 matrix rows with a warp per block
+// row; 23 us per 10^6 rows since short block rows are bundled four to a warp, i.e. a block row costs as much as ~330 bytes of
+// streaming).
 __global__ void spmv_weight_kernel(const int32_t* __restrict__ brp, const uint32_t* __restrict__ rvb, int nbr, int vsize,
                                    uint64_t row_cost, uint64_t* __restrict__ w) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,7 +62,7 @@ extern "C" int bmsp_partition_block_rows(bmsp_matrix_t A, bmsp_matrix_t Bt, int3
     if (weight_spgemm) cand_weight_kernel<<<(unsigned)ceil_div(nbr, 8), 256, 0, st>>>(A->brp, A->bcol, Bt->brp, nbr, w);
     else {
         const bool blockpar = A->nblk > 0 && (double)A->nnz / (double)A->nblk < 2.5;      // same rule as plan_spmv
-        spmv_weight_kernel<<<(unsigned)ceil_div(nbr, 256), 256, 0, st>>>(A->brp, A->rvb, nbr, A->dtype == BMSP_F16 ? 2 : 4, blockpar ? 600 : 40, w);
+        spmv_weight_kernel<<<(unsigned)ceil_div(nbr, 256), 256, 0, st>>>(A->brp, A->rvb, nbr, A->dtype == BMSP_F16 ? 2 : 4, blockpar ? 330 : 40, w);
     }
     BMSP_KERNEL_CHECK();
     BMSP_TRY(exclusive_scan_u64(w, w, nbr, st));

@@ -33,6 +33,10 @@ struct GemmArgs {
     const int32_t* a_brp; const int32_t* a_bcol; const uint64_t* a_bmps; const uint8_t* a_kmask; const uint64_t* a_off; const __half* a_val;
     const int32_t* b_brp; const int32_t* b_bcol; const uint64_t* b_bmps; const uint8_t* b_kmask; const uint64_t* b_off; const __half* b_val;
     const uint4* b_pm;         // packed per-B-block records, two uint4 each: {bitmap lo, bitmap hi, block column, value offset}, {first 8 values}
+    // fine index of B (sparse-block operands; null: candidate scan): bucket (k, t) = the blocks of B's block row k whose kmask has
+    // bit t, i.e. that have something in row 8k + (inner index of bit t).  An A block with kmask `am` meets exactly the blocks of
+    // the buckets (bcol(a), t), t in am -- read as contiguous runs instead of found by testing every block of the B block row.
+    const uint32_t* f_ptr; const uint32_t* f_bcol; const uint8_t* f_kmask; const uint4* f_rec;
     const int2* rowinfo;       // per A block row: x = first C block column of the bit set (multiple of 32), y = words
     int32_t row_begin, row_end;
     int32_t G;                 // lanes cooperating on one A block (power of two <= 32)
@@ -124,13 +128,14 @@ __global__ void __launch_bounds__(256) rowinfo_kernel(const int32_t* __restrict_
                                                       const int32_t* __restrict__ b_brp, const int32_t* __restrict__ b_bcol,
                                                       int row_begin, int row_end, int2* __restrict__ rowinfo,
                                                       unsigned long long* __restrict__ cand, int* __restrict__ maxes,
-                                                      unsigned long long* __restrict__ sum_words, unsigned long long* __restrict__ max_cand) {
-    __shared__ unsigned long long s_words, s_maxc;
+                                                      unsigned long long* __restrict__ sum_words, unsigned long long* __restrict__ max_cand,
+                                                      unsigned long long* __restrict__ sum_cand) {
+    __shared__ unsigned long long s_words, s_maxc, s_cand;
     __shared__ int s_maxw;
     const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) { s_words = 0; s_maxc = 0; s_maxw = 0; }
+    if (threadIdx.x == 0) { s_words = 0; s_maxc = 0; s_maxw = 0; s_cand = 0; }
     __syncthreads();
-    unsigned long long w_sum = 0, w_maxc = 0;
+    unsigned long long w_sum = 0, w_maxc = 0, w_cand = 0;
     int w_maxw = 0;
     for (int row = row_begin + blockIdx.x * 8 + (threadIdx.x >> 5); row < row_end; row += gridDim.x * 8) {
         int jmin = 0x7FFFFFFF, jmax = -1;
@@ -154,15 +159,16 @@ __global__ void __launch_bounds__(256) rowinfo_kernel(const int32_t* __restrict_
             if (jmax >= 0) { jbase = jmin & ~31; words = ((jmax - jbase) >> 5) + 1; }
             rowinfo[row - row_begin] = make_int2(jbase, words);
             cand[row - row_begin] = c;
-            w_maxw = max(w_maxw, words); w_sum += (unsigned long long)words; w_maxc = max(w_maxc, c);
+            w_maxw = max(w_maxw, words); w_sum += (unsigned long long)words; w_maxc = max(w_maxc, c); w_cand += c;
         }
     }
-    if (lane == 0) { atomicMax(&s_maxw, w_maxw); atomicAdd(&s_words, w_sum); atomicMax(&s_maxc, w_maxc); }
+    if (lane == 0) { atomicMax(&s_maxw, w_maxw); atomicAdd(&s_words, w_sum); atomicMax(&s_maxc, w_maxc); atomicAdd(&s_cand, w_cand); }
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_maxw) atomicMax(maxes, s_maxw);
         if (s_words) atomicAdd(sum_words, s_words);
         if (s_maxc) atomicMax(max_cand, s_maxc);
+        if (s_cand) atomicAdd(sum_cand, s_cand);
     }
 }
 
@@ -439,6 +445,40 @@ __device__ __forceinline__ void enumerate_vec(const GemmArgs& g, const RowCtx& r
     }
 }
 
+// ---- fine index of B ---------------------------------------------------------------------------------------------
+// Uniform-random and R-MAT operands have about one value per 8x8 block.  The candidate scan then tests every block of B's block
+// row bcol(a) against the A block (U1M: 128 tests for 16 survivors) and fetches each survivor's record with a random access: one
+// 64-byte DRAM burst per pair and pass (ncu, U1M: 31 GB read by FILL, 31 GB by NUMERIC, for 12 GB of algorithmic bytes).  With
+// B's blocks bucketed by inner index the survivors of an A block are the contiguous bucket(s) of its own inner index(es).
+__global__ void fine_max_kernel(const uint32_t* __restrict__ cnt, int64_t n, uint32_t* __restrict__ mx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = i < n ? cnt[i] : 0u;
+    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(mx, v);
+}
+__global__ void fine_count_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ kmask, int64_t nblk, uint32_t* __restrict__ cnt) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const uint32_t br = (uint32_t)(keys[b] >> 32);
+    uint32_t m = kmask[b];
+    while (m) { const int t = __ffs(m) - 1; m &= m - 1; atomicAdd(cnt + (size_t)br * 8 + t, 1u); }
+}
+// one thread per bucket walks its block row in order: entries of a bucket keep the block order (deterministic)
+__global__ void fine_fill_kernel(const int32_t* __restrict__ brp, const uint8_t* __restrict__ kmask, const uint4* __restrict__ pm, int32_t nbr,
+                                 const uint32_t* __restrict__ fptr, uint32_t* __restrict__ f_bcol, uint8_t* __restrict__ f_kmask, uint4* __restrict__ f_rec) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= (int64_t)nbr * 8) return;
+    const int br = (int)(u >> 3), t = (int)(u & 7);
+    uint32_t w = fptr[u];
+    for (int b = brp[br]; b < brp[br + 1]; b++) {
+        const uint32_t km = kmask[b];
+        if (!((km >> t) & 1u)) continue;
+        const uint4 r0 = pm[2 * (int64_t)b], r1 = pm[2 * (int64_t)b + 1];
+        f_bcol[w] = r0.z; f_kmask[w] = (uint8_t)km; f_rec[2 * (int64_t)w] = r0; f_rec[2 * (int64_t)w + 1] = r1;
+        w++;
+    }
+}
+
 // CTA-wide exclusive scan of popc(bmp[c]), c < n: writes the 64-bit prefix to off[c] and returns the total.
 __device__ __forceinline__ uint32_t scan_popc64(const uint64_t* bmp, uint64_t* off, int n, uint32_t* s_tmp) {
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -522,6 +562,103 @@ __device__ __forceinline__ void enumerate_row(const GemmArgs& g, const RowCtx& r
     if (MODE != MODE_SETBITS) {
         drain<MODE>(g, r, q, qn);
         __syncwarp();
+    }
+}
+
+// Walk the surviving pairs of a work item through B's fine index: 8 lanes per A block, one bucket per bit of its kmask, the
+// lanes striding over the bucket, two entries in flight per lane.  A B block that shares several inner indices with the A block
+// sits in several of those buckets; it is taken from the lowest one.  Buckets longer than FINE_LONG entries (the hub rows of a
+// power-law B) are left to a second walk with a whole warp per bucket -- eight lanes on a 10^4-entry bucket would be the tail of
+// the row.
+//   FMODE 0: set the C block column's bit (f_bcol / f_kmask only: 5 bytes per pair), count survivors when STATS
+//   FMODE 1: OR the pair's boolean block product into the C block's bitmap          (32-byte record)
+//   FMODE 2: multiply                                                                 (32-byte record, values inline)
+// CTA-wide: every thread of the CTA must call it (it synchronises).
+constexpr int FINE_LONG = 256;
+template <int FMODE, bool STATS>
+__device__ __forceinline__ void fine_entry(const GemmArgs& g, const RowCtx& r, int a, int rl, int jb, int wb, uint64_t abmp, uint32_t aoff, uint32_t f,
+                                           uint32_t& cnt) {
+    if (FMODE == 0) {
+        const int j = (int)g.f_bcol[f] - jb;
+        atomicOr(&r.bitset[wb + (j >> 5)], 1u << (j & 31));
+        cnt++;
+    } else {
+        PairIn in;
+        in.pm = __ldg(g.f_rec + 2 * (int64_t)f);
+        in.bv8 = FMODE == 2 ? __ldg(g.f_rec + 2 * (int64_t)f + 1) : make_uint4(0, 0, 0, 0);
+        in.abmp = abmp; in.aoff = aoff;
+        apply_pair<FMODE == 1 ? MODE_FILL : MODE_NUMERIC>(g, r, a, in);
+    }
+}
+template <int FMODE, bool STATS>
+__device__ __forceinline__ void fine_bucket(const GemmArgs& g, const RowCtx& r, int a, int rl, uint32_t am, uint32_t below, uint64_t abmp, uint32_t aoff,
+                                            uint32_t f0, uint32_t f1, uint32_t first, uint32_t step, uint32_t& cnt) {
+    const int jb = r.jb[rl], wb = r.wo[rl];
+    uint32_t f = f0 + first;
+    if constexpr (FMODE == 0) {
+        for (; f < f1; f += step) {
+            if (below && (g.f_kmask[f] & below)) continue;                 // already met in a lower bucket
+            fine_entry<FMODE, STATS>(g, r, a, rl, jb, wb, abmp, aoff, f, cnt);
+        }
+    } else {
+    // two records in flight per lane: the loads of entries f and f + step are issued before either is used
+    for (; f + step < f1; f += 2 * step) {
+        const bool s0 = !(below && (g.f_kmask[f] & below)), s1 = !(below && (g.f_kmask[f + step] & below));
+        PairIn i0, i1;
+        i0.abmp = i1.abmp = abmp; i0.aoff = i1.aoff = aoff;
+        i0.pm = i1.pm = make_uint4(0, 0, 0, 0); i0.bv8 = i1.bv8 = make_uint4(0, 0, 0, 0);
+        if (s0) { i0.pm = __ldg(g.f_rec + 2 * (int64_t)f); if (FMODE == 2) i0.bv8 = __ldg(g.f_rec + 2 * (int64_t)f + 1); }
+        if (s1) { i1.pm = __ldg(g.f_rec + 2 * (int64_t)(f + step)); if (FMODE == 2) i1.bv8 = __ldg(g.f_rec + 2 * (int64_t)(f + step) + 1); }
+        if (s0) apply_pair<FMODE == 1 ? MODE_FILL : MODE_NUMERIC>(g, r, a, i0);
+        if (s1) apply_pair<FMODE == 1 ? MODE_FILL : MODE_NUMERIC>(g, r, a, i1);
+    }
+    if (f < f1 && !(below && (g.f_kmask[f] & below))) fine_entry<FMODE, STATS>(g, r, a, rl, jb, wb, abmp, aoff, f, cnt);
+    }
+}
+template <int FMODE, bool STATS>
+__device__ __forceinline__ void enumerate_fine(const GemmArgs& g, const RowCtx& r, uint32_t& n_surv) {
+    constexpr int GL = 8;
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = T >> 5;
+    const int slots = T / GL, slot = tid / GL, gl = tid % GL;
+    bool any_long = false;
+    for (int a = r.a0 + slot; a < r.a1; a += slots) {
+        const int k = g.a_bcol[a];
+        const uint32_t am = g.a_kmask[a];
+        const int rl = local_row(r.abr, r.nr, a);
+        uint64_t abmp = 0; uint32_t aoff = 0;
+        if (FMODE >= 1) abmp = g.a_bmps[a];
+        if (FMODE == 2) aoff = (uint32_t)g.a_off[a];
+        uint32_t m = am, cnt = 0;
+        while (m) {
+            const int t = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t f0 = g.f_ptr[(size_t)k * 8 + t], f1 = g.f_ptr[(size_t)k * 8 + t + 1];
+            if (f1 - f0 > FINE_LONG) { any_long = true; continue; }       // second walk below
+            fine_bucket<FMODE, STATS>(g, r, a, rl, am, am & ((1u << t) - 1u), abmp, aoff, f0, f1, gl, GL, cnt);
+        }
+        if (STATS && cnt) { n_surv += cnt; if (r.nr > 1) atomicAdd(&r.rsurv[rl], cnt); }
+    }
+    // long buckets: warp w takes the A blocks a0 + w, a0 + w + nwarps, ...; its 32 lanes stride over the bucket.  The walk is
+    // warp-uniform (every lane sees the same A block and bit), so nothing has to be handed over between lanes.
+    if (!__syncthreads_or(any_long)) return;
+    for (int a = r.a0 + wid; a < r.a1; a += nwarps) {
+        const int k = g.a_bcol[a];
+        const uint32_t am = g.a_kmask[a];
+        uint32_t m = am, cnt = 0;
+        int rl = -1; uint64_t abmp = 0; uint32_t aoff = 0;
+        while (m) {
+            const int t = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t f0 = g.f_ptr[(size_t)k * 8 + t], f1 = g.f_ptr[(size_t)k * 8 + t + 1];
+            if (f1 - f0 <= FINE_LONG) continue;
+            if (rl < 0) {
+                rl = local_row(r.abr, r.nr, a);
+                if (FMODE >= 1) abmp = g.a_bmps[a];
+                if (FMODE == 2) aoff = (uint32_t)g.a_off[a];
+            }
+            fine_bucket<FMODE, STATS>(g, r, a, rl, am, am & ((1u << t) - 1u), abmp, aoff, f0, f1, (uint32_t)lane, 32u, cnt);
+        }
+        if (STATS && cnt) { n_surv += cnt; if (r.nr > 1) atomicAdd(&r.rsurv[rl], cnt); }
     }
 }
 
@@ -620,7 +757,8 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
         if (PASS == PASS_COUNT) {
             __syncthreads();
             uint32_t ns = 0;
-            enumerate_vec<false, true>(g, r, nullptr, nullptr, n_cand, ns);      // bits; survivors per row into s_rsurv
+            if (g.f_ptr) enumerate_fine<0, true>(g, r, ns);
+            else enumerate_vec<false, true>(g, r, nullptr, nullptr, n_cand, ns);      // bits; survivors per row into s_rsurv
             n_surv_total += ns;
             if (nr == 1) {
 #pragma unroll
@@ -646,6 +784,13 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
             if (cfit) for (int c = tid; c < ccount; c += T) r.cbmp[c] = 0;
             __syncthreads();
             uint32_t ns = 0;
+            if (g.f_ptr) {
+                // fine index: no pair list at all -- bits from the 5-byte bucket entries, then the records once
+                enumerate_fine<0, false>(g, r, ns);
+                __syncthreads();
+                rank_words(r.bitset, r.wrank, nwords, s_tmp);
+                enumerate_fine<1, false>(g, r, ns);
+            } else {
             // pair list only: a survivor's C block column comes with its packed B record (one sector, fetched here for the first time
             // and again -- from L2 -- by the pair pass below) instead of a separate random read of b_bcol per survivor
             enumerate_vec<true, false, false>(g, r, list, s_cursor, n_cand, ns);
@@ -659,6 +804,7 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
             __syncthreads();
             rank_words(r.bitset, r.wrank, nwords, s_tmp);
             for (uint32_t e = tid; e < nsurv; e += T) { const uint2 pr = list[e]; process_pair<MODE_FILL>(g, r, (int)pr.x, (int)pr.y); }
+            }
             __syncthreads();
             // keys, bitmaps and the derived per-block arrays out: ascending (row, bit index) = ascending key
             for (int w = tid; w < nwords; w += T) {
@@ -712,7 +858,10 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
             }
             __syncthreads();
             rank_words(r.bitset, r.wrank, nwords, s_tmp);
-            if (PASS == PASS_NUMERIC) {
+            if (PASS == PASS_NUMERIC && g.f_ptr) {
+                uint32_t ns = 0;
+                enumerate_fine<2, false>(g, r, ns);
+            } else if (PASS == PASS_NUMERIC) {
                 if (g.split8) {
                     for (uint64_t e = tid; e < (uint64_t)nsurv * 8u; e += T) { const uint2 pr = list[e >> 3]; process_pair<MODE_NUMERIC>(g, r, (int)pr.x, (int)pr.y, (int)(e & 7u)); }
                 } else if (MAXT == 1024) {            // 32 registers per thread: one pair at a time
@@ -761,6 +910,123 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) { n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o); n_surv_total += __shfl_xor_sync(0xffffffffu, n_surv_total, o); }
         if (lane == 0) { atomicAdd(g.stats, n_cand); atomicAdd(g.stats + 1, n_surv_total); }
+    }
+}
+
+// ---- dense-block numeric pass, narrow rows (block-clustered / banded operands) -------------------------------------------------
+// The generic mma.sync pass above fetches every fragment element with its own rank + 2-byte global load (two dependent latencies
+// per fragment, 32 scattered loads) and keeps 12 two-warp CTAs per SM busy at 19 % warps active (ncu, round 1: BC4M 18.5 ms).
+// Here one warp owns a block row.  A block's compact values are read ONCE, coalesced (lane l takes values l and l + 32 of the
+// block, packed in one register); a fragment element is then a rank (shift + popc) and a warp shuffle -- no dependent load.  Two
+// B^t blocks are stacked as the 16x8 A-operand of mma.m16n8k8, the A block is the B-operand, D = the two 8x8 products transposed;
+// each lane owns two fixed slots of every dense C block in shared memory, so the accumulation needs no atomics.  The loads of the
+// next pair of B blocks are issued before the current MMA.  C block index of a pair: a per-row table over the row's column span.
+struct DenseArgs {
+    const int32_t* c_brp;      // [nrows+1] C block-row pointers (row - row_begin)
+    const uint64_t* row_nnz;   // [nrows+1] value base of every row
+    int32_t wcols;             // C block columns per window: a warp's accumulators cover wcols dense blocks (wcols * 256 bytes)
+};
+
+// values l and l + 32 of a block (cnt values from vals + off) in one register: low half = value l, high half = value l + 32
+__device__ __forceinline__ uint32_t load_block_vals(const __half* __restrict__ vals, uint32_t off, int cnt, int lane) {
+    const unsigned short lo = lane < cnt ? __half_as_ushort(__ldg(vals + off + lane)) : (unsigned short)0;
+    const unsigned short hi = lane + 32 < cnt ? __half_as_ushort(__ldg(vals + off + 32 + lane)) : (unsigned short)0;
+    return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+// fragment register for cells p0, p0 + 1 of a block whose values sit in the warp as packed by load_block_vals
+__device__ __forceinline__ uint32_t frag_shfl(uint64_t bmp, uint32_t packed, int p0) {
+    const uint32_t two = (uint32_t)(bmp >> (62 - p0)) & 3u;        // bit1 = cell p0, bit0 = cell p0+1
+    const int r0 = rank64(bmp, p0), r1 = r0 + (int)(two >> 1);
+    const uint32_t w0 = __shfl_sync(0xffffffffu, packed, r0 & 31), w1 = __shfl_sync(0xffffffffu, packed, r1 & 31);
+    const uint32_t v0 = (r0 & 32) ? (w0 >> 16) : (w0 & 0xFFFFu), v1 = (r1 & 32) ? (w1 >> 16) : (w1 & 0xFFFFu);
+    return ((two & 2u) ? v0 : 0u) | (((two & 1u) ? v1 : 0u) << 16);
+}
+
+// One warp per block row; the row's C block columns are covered in windows of `wcols` columns so that a warp's dense accumulators
+// stay small (wcols = 16: 4 KB per warp, 48 warps per SM; with all of a 63-column row resident the SM held 12 warps and the pass
+// waited on its own loads: 23.7 ms).  Per A block the lanes test the B block row in parallel (block column inside the window,
+// inner-dimension masks overlap) and the survivors are taken two at a time off the ballot.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) spgemm_dense_kernel(GemmArgs g, DenseArgs da) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int wcols = da.wcols;
+    float* s_dense = reinterpret_cast<float*>(smem) + (size_t)wid * wcols * 64;
+    const int p0 = (lane >> 2) * 8 + (lane & 3) * 2;
+    const int P0 = (lane & 3) * 16 + (lane >> 2);          // slot L <-> cell (r = 2t, c = g), slot L + 32 <-> (2t + 1, g)
+    const int nrows = g.row_end - g.row_begin;
+    for (;;) {
+        int lrow = 0;
+        if (lane == 0) lrow = atomicAdd(g.work_counter, 1);
+        lrow = __shfl_sync(0xffffffffu, lrow, 0);
+        if (lrow >= nrows) break;
+        const int row = g.row_begin + lrow;
+        const int c0 = da.c_brp[lrow], ccount = da.c_brp[lrow + 1] - c0;
+        if (ccount == 0) continue;
+        const uint64_t vbase = da.row_nnz[lrow];
+        for (int c = lane; c < ccount; c += 32) g.c_off[c0 + c] += vbase;       // FILL left row-relative offsets: absolute from here on
+        const int jfirst = g.c_bcol[c0], jlast = g.c_bcol[c0 + ccount - 1];
+        const int a0 = g.a_brp[row], a1 = g.a_brp[row + 1];
+        int cdone = 0;                                                           // C blocks of the windows already stored
+        for (int jw = jfirst; jw <= jlast; jw += wcols) {
+            for (int v = lane; v < wcols * 64; v += 32) s_dense[v] = 0.f;
+            __syncwarp();
+            for (int a = a0; a < a1; a++) {
+                const int k = g.a_bcol[a];
+                const uint32_t am = g.a_kmask[a];
+                const int b0 = g.b_brp[k], b1 = g.b_brp[k + 1];
+                uint32_t fb = 0; bool have_fb = false;
+                for (int bb = b0; bb < b1; bb += 32) {
+                    const int b = bb + lane;
+                    bool in = false;
+                    if (b < b1) { const int j = g.b_bcol[b] - jw; in = j >= 0 && j < wcols && (am & g.b_kmask[b]) != 0; }
+                    uint32_t mask = __ballot_sync(0xffffffffu, in);
+                    if (!mask) continue;
+                    if (!have_fb) {
+                        const uint64_t abmp = g.a_bmps[a];
+                        fb = frag_shfl(abmp, load_block_vals(g.a_val, (uint32_t)g.a_off[a], __popcll(abmp), lane), p0);
+                        have_fb = true;
+                    }
+                    // survivors two at a time; the record and the values of the next pair are loaded before this pair's MMA
+                    auto take = [&](uint4& rec, uint32_t& pk) {
+                        const int l = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        rec = __ldg(g.b_pm + 2 * (int64_t)(bb + l));
+                        pk = load_block_vals(g.b_val, rec.w, __popc(rec.x) + __popc(rec.y), lane);
+                    };
+                    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, n0 = r0, n1 = r0; uint32_t k0 = 0, k1 = 0, m0 = 0, m1 = 0;
+                    bool two = false, ntwo = false, more;
+                    take(r0, k0);
+                    if (mask) { take(r1, k1); two = true; }
+                    for (;;) {
+                        more = mask != 0;
+                        if (more) { take(n0, m0); ntwo = mask != 0; if (ntwo) take(n1, m1); }
+                        const uint32_t fa0 = frag_shfl(((uint64_t)r0.y << 32) | r0.x, k0, p0);
+                        const uint32_t fa1 = two ? frag_shfl(((uint64_t)r1.y << 32) | r1.x, k1, p0) : 0u;
+                        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                                     : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(fa0), "r"(fa1), "r"(fb));
+                        float* q0 = s_dense + ((int)r0.z - jw) * 64 + lane;
+                        q0[0] += d0; q0[32] += d1;
+                        if (two) { float* q1 = s_dense + ((int)r1.z - jw) * 64 + lane; q1[0] += d2; q1[32] += d3; }
+                        if (!more) break;
+                        r0 = n0; k0 = m0; r1 = n1; k1 = m1; two = ntwo;
+                    }
+                }
+            }
+            __syncwarp();
+            // the window's C blocks out: compact the dense accumulators through C's bitmaps
+            while (cdone < ccount) {
+                const int j = g.c_bcol[c0 + cdone] - jw;
+                if (j >= wcols) break;
+                const uint64_t bmp = g.c_bmps[c0 + cdone];
+                float* dst = g.c_val + g.c_off[c0 + cdone];
+                if ((bmp >> (63 - P0)) & 1ull) dst[rank64(bmp, P0)] = s_dense[j * 64 + lane];
+                if ((bmp >> (55 - P0)) & 1ull) dst[rank64(bmp, P0 + 8)] = s_dense[j * 64 + 32 + lane];
+                cdone++;
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -837,7 +1103,10 @@ struct RowSplit {
 
 template <int PASS>
 static int launch_pass(GemmArgs& g, int T, int sms, cudaStream_t st, const RowSplit& sp) {
-    if (!sp.active) return launch_pass_t<PASS, 256>(g, T, sms, (int)ceil_div(g.row_end - g.row_begin, g.group), st);
+    if (!sp.active) {
+        if (T > 256) return launch_pass_t<PASS, 1024>(g, T, sms, (int)ceil_div(g.row_end - g.row_begin, g.group), st);
+        return launch_pass_t<PASS, 256>(g, T, sms, (int)ceil_div(g.row_end - g.row_begin, g.group), st);
+    }
     GemmArgs gh = g, gl = g;
     gh.group = gl.group = 1;
     gh.row_list = sp.list; gh.n_list = sp.n_heavy; gh.work_counter = g.work_counter + 1; gh.G = 32; gh.batch = 1;
@@ -901,18 +1170,19 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
 
     SG_TRY(dev_alloc_t(&rowinfo, (size_t)nrows + 1, st));
     SG_TRY(dev_alloc_t(&cand, (size_t)nrows + 1, st));
-    SG_TRY(dev_alloc_t(&small, 16, st));
+    SG_TRY(dev_alloc_t(&small, 24, st));
     SG_TRY(dev_alloc_t(&row_count, (size_t)nrows + 2, st));
     SG_TRY(dev_alloc_t(&row_surv, (size_t)nrows + 2, st));
     SG_TRY(dev_alloc_t(&row_nnz, (size_t)nrows + 2, st));
-    SG_CUDA(cudaMemsetAsync(small, 0, 16 * sizeof(int32_t), st));
+    SG_CUDA(cudaMemsetAsync(small, 0, 24 * sizeof(int32_t), st));
     int32_t* maxes = small; int32_t* counter = small + 4; unsigned long long* stats = (unsigned long long*)(small + 8);
     unsigned long long* sum_words = (unsigned long long*)(small + 12);
     unsigned long long* max_cand = (unsigned long long*)(small + 14);
+    unsigned long long* sum_cand = (unsigned long long*)(small + 16);
 
-    int32_t h_small[16] = {0};
+    int32_t h_small[24] = {0};
     if (nrows > 0) {
-        rowinfo_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nrows, 8), (int64_t)sms * 8), 256, 0, st>>>(A->brp, A->bcol, Bt->brp, Bt->bcol, rb, re, rowinfo, cand, maxes, sum_words, max_cand);
+        rowinfo_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nrows, 8), (int64_t)sms * 8), 256, 0, st>>>(A->brp, A->bcol, Bt->brp, Bt->bcol, rb, re, rowinfo, cand, maxes, sum_words, max_cand, sum_cand);
         SG_CUDA(cudaGetLastError());
     }
     SG_CUDA(cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
@@ -961,7 +1231,7 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     int group = 1;
     if (avg_cand <= 96 && !sp.active && (int64_t)16 * max_words <= 8192) group = 16;
     if (const char* e = getenv("BMSP_SPGEMM_GROUP")) { const int v = atoi(e); if (v >= 1 && v <= 32 && !sp.active && (int64_t)v * max_words <= 8192) group = v; }
-    const int T = group > 1 ? 128 : (avg_cand <= 96 ? 32 : (avg_cand <= 2048 ? 128 : 256));
+    int T = group > 1 ? 128 : (avg_cand <= 96 ? 32 : (avg_cand <= 2048 ? 128 : 256));
     if (G > T) G = T;
 
     if (!Bt->pmeta && Bt->nblk > 0) {      // built once per B operand, reused by later products
@@ -970,8 +1240,55 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
                                                                           (uint4*)Bt->pmeta, Bt->nblk);
         SG_CUDA(cudaGetLastError());
     }
+    // Fine index of B for sparse-block operands (about one value per block: uniform random, R-MAT): built once per B operand.
+    {
+        static const int fine_env = [] { const char* e = getenv("BMSP_SPGEMM_FINE"); return e ? atoi(e) : -1; }();      // 0 / 1 force it off / on
+        const double dAq = A->nblk ? (double)A->nnz / A->nblk : 0.0, dBq = Bt->nblk ? (double)Bt->nnz / Bt->nblk : 0.0;
+        const bool want = fine_env >= 0 ? fine_env == 1 : (dBq <= 2.0 && dAq <= 4.0);
+        if (want && Bt->fine_state == 0 && Bt->nblk > 0 && (int64_t)Bt->nbr * 8 + 1 < 0x7FFFFFFFll) {
+            uint32_t* fp = nullptr;
+            SG_TRY(dev_alloc_t(&fp, (size_t)Bt->nbr * 8 + 2, st));
+            SG_CUDA(cudaMemsetAsync(fp, 0, sizeof(uint32_t) * ((size_t)Bt->nbr * 8 + 2), st));
+            fine_count_kernel<<<(unsigned)ceil_div(Bt->nblk, 256), 256, 0, st>>>(Bt->keys, Bt->kmask, Bt->nblk, fp);
+            SG_CUDA(cudaGetLastError());
+            // the longest bucket (read back with the total below): slot nbr * 8 + 1 of the zeroed array
+            fine_max_kernel<<<(unsigned)ceil_div((int64_t)Bt->nbr * 8, 256), 256, 0, st>>>(fp, (int64_t)Bt->nbr * 8, fp + (size_t)Bt->nbr * 8 + 1);
+            SG_CUDA(cudaGetLastError());
+            uint32_t longest = 0;
+            if (cudaMemcpyAsync(&longest, fp + (size_t)Bt->nbr * 8 + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) status = BMSP_ERR_CUDA;
+            status = exclusive_scan_u32(fp, fp, (int64_t)Bt->nbr * 8, st);
+            uint32_t total = 0;
+            if (status == BMSP_OK && cudaMemcpyAsync(&total, fp + (size_t)Bt->nbr * 8, sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) status = BMSP_ERR_CUDA;
+            if (status == BMSP_OK && cudaStreamSynchronize(st) != cudaSuccess) status = BMSP_ERR_CUDA;
+            if (status != BMSP_OK) { dev_free(fp, st); return fail(status); }
+            // worth it while the buckets replicate little (a block with m inner indices sits in m buckets) and are of similar length:
+            // a power-law B (R-MAT) has hub buckets of 10^4 entries next to a mean of 2, and the candidate scan, which spreads a B block
+            // row over up to 32 lanes, handles those better (R-MAT-18 A*A: 164 ms by scan, 181 ms through the buckets)
+            const double mean_bucket = (double)total / std::max<double>(1.0, (double)Bt->nbr * 8);
+            const bool even = (double)longest <= 32.0 * std::max(mean_bucket, 1.0) || longest <= 512;
+            if (((double)total <= 1.5 * (double)Bt->nblk && even) || fine_env == 1) {
+                Bt->fine_ptr = fp; Bt->fine_n = total;
+                SG_TRY(dev_alloc_t(&Bt->fine_bcol, (size_t)total + 4, st));
+                SG_TRY(dev_alloc_t(&Bt->fine_kmask, (size_t)total + 16, st));
+                SG_TRY(dev_alloc((void**)&Bt->fine_rec, 2 * sizeof(uint4) * ((size_t)total + 1), st));
+                fine_fill_kernel<<<(unsigned)ceil_div((int64_t)Bt->nbr * 8, 128), 128, 0, st>>>(Bt->brp, Bt->kmask, (const uint4*)Bt->pmeta, Bt->nbr, fp, Bt->fine_bcol,
+                                                                                             Bt->fine_kmask, (uint4*)Bt->fine_rec);
+                SG_CUDA(cudaGetLastError());
+                Bt->fine_state = 1;
+            } else { dev_free(fp, st); Bt->fine_state = -1; }
+        }
+        if (!want && fine_env == 0) {}
+    }
+    const bool use_fine = Bt->fine_state == 1 && [] { const char* e = getenv("BMSP_SPGEMM_FINE"); return !e || atoi(e) != 0; }();
+    // Walking B's fine index a row's passes wait on record loads and are held to 3-4 CTAs per SM by the row's bit set in shared
+    // memory: more threads per CTA are more loads in flight for the same shared memory
+    if (use_fine && T == 256 && !sp.active) {
+        static const int t_env = [] { const char* e = getenv("BMSP_SPGEMM_T"); return e ? atoi(e) : 512; }();
+        if (t_env == 256 || t_env == 512 || t_env == 1024) T = t_env;
+    }
     GemmArgs g;
     memset(&g, 0, sizeof(g));
+    if (use_fine) { g.f_ptr = Bt->fine_ptr; g.f_bcol = Bt->fine_bcol; g.f_kmask = Bt->fine_kmask; g.f_rec = (const uint4*)Bt->fine_rec; }
     g.b_pm = (const uint4*)Bt->pmeta;
     g.a_brp = A->brp; g.a_bcol = A->bcol; g.a_bmps = A->bmps; g.a_kmask = A->kmask; g.a_off = A->offsets; g.a_val = (const __half*)A->values;
     g.b_brp = Bt->brp; g.b_bcol = Bt->bcol; g.b_bmps = Bt->bmps; g.b_kmask = Bt->kmask; g.b_off = Bt->offsets; g.b_val = (const __half*)Bt->values;
@@ -1010,6 +1327,7 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     if (verbose) SG_CUDA(cudaEventRecord(ev[3], st));
     unsigned long long h_stats[2];
     memcpy(h_stats, h_small + 8, sizeof(h_stats));
+    if (use_fine) memcpy(&h_stats[0], h_small + 16, sizeof(unsigned long long));     // the fine walk never sees the pairs it skips: candidates from P0
     if (c_size > 0x7FFFFFFFll || h_stats[1] > 0xFFFFFFFFull) {
         set_error("product too large for one call: %lld C blocks, %llu surviving pairs (shard A's block rows with brow_begin/brow_end)",
                   (long long)c_size, h_stats[1]);
@@ -1025,7 +1343,7 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     SG_TRY(dev_alloc_t(&C->kmask, (size_t)c_size + 16, st));
     SG_TRY(dev_alloc_t(&C->brp, (size_t)C->nbr + 1 + 8, st));
     SG_TRY(dev_alloc_t(&C->rvb, (size_t)C->nbr + 1 + 8, st));
-    SG_TRY(dev_alloc_t(&surv_list, (size_t)n_surv + 1, st));
+    SG_TRY(dev_alloc_t(&surv_list, use_fine ? (size_t)1 : (size_t)n_surv + 1, st));
     g.c_brp = (const int32_t*)row_count; g.c_keys = C->keys; g.c_bmps = C->bmps; g.c_bcol = C->bcol; g.c_kmask = C->kmask;
     g.c_off = C->offsets; g.surv_list = surv_list;
 
@@ -1056,7 +1374,25 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     int path = opts ? opts->numeric_path : -1;
     if (path < 0) path = (dA * dB / 8.0 >= 40.0) ? 1 : 0;
     if (c_nnz > 0) {
-        if (path == 1) {
+        static const int dense_env = [] { const char* e = getenv("BMSP_SPGEMM_DENSE"); return e ? atoi(e) : 1; }();
+        const int max_c_row0 = std::max(1, h_small[3]);
+        if (path == 1 && dense_env && !sp.active && (int64_t)max_words * 32 <= 1024) {
+            // narrow rows of dense blocks: one warp per block row, dense accumulators for a window of C columns in shared memory
+            constexpr int WARPS = 4;
+            DenseArgs da;
+            static const int wc_env = [] { const char* e = getenv("BMSP_SPGEMM_WCOLS"); return e ? atoi(e) : 16; }();
+            da.c_brp = (const int32_t*)row_count; da.row_nnz = row_nnz; da.wcols = std::max(8, std::min(wc_env, 64));
+            const size_t smem = (size_t)WARPS * (size_t)da.wcols * 256;
+            auto kern = spgemm_dense_kernel<WARPS>;
+            SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+            int occ = 0;
+            SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+            if (occ < 1) { set_error("spgemm dense pass does not fit: smem %zu", smem); return fail(BMSP_ERR_CUDA); }
+            SG_CUDA(cudaMemsetAsync(g.work_counter, 0, sizeof(int32_t), st));
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * occ, ceil_div(nrows, WARPS)));
+            kern<<<grid, WARPS * 32, smem, st>>>(g, da);
+            SG_CUDA(cudaGetLastError());
+        } else if (path == 1) {
             const int max_c_row = std::max(1, h_small[3]);                         // recorded by COUNT
             g.cap_c = std::min(max_c_row, 192);
             if (max_c_row > g.cap_c) SG_CUDA(cudaMemsetAsync(C->values, 0, (size_t)c_nnz * 4, st));

@@ -223,6 +223,7 @@ struct TileArgs {
     const TileDesc* desc; const uint32_t* lines; const uint16_t* xoff;
     int32_t rows, nbr, cols, cap_blk, cap_val, cap_lines;
     int32_t tile0;       // first tile of this launch (row-range launches of the host-buffer pipeline)
+    const int32_t* tile_list;   // streaming kernel: when set, the launch's q-th tile is tile_list[q] (boundary / interior launches of the multi-GPU product)
     TileSmem so;
 };
 
@@ -446,6 +447,8 @@ struct HaloDev {
     uint32_t* scratch;                       // [0] pushing CTAs that finished, [1] error: a wait timed out
     uint32_t wait_epoch, signal_epoch, n_sig;
     int32_t solo_tile;                       // tile that signals when no tile pushes anything (-1: none)
+    int32_t n_iv, iv_lo[HALO_MAX], iv_hi[HALO_MAX];   // the tiles that own pushed rows, as disjoint tile intervals [lo, hi] (host-computed:
+                                             // the streaming kernel's producer tests a tile against these instead of the row ranges)
     int32_t own_c0, own_c1;                  // columns [own_c0, own_c1) of x_ext are this rank's own slice: tiles that stay inside never wait
     int32_t rot;                             // tile order rotation: CTA b runs tile (b + rot) mod ntiles, so that the boundary tiles
                                              // (which need the peers' rows and produce the rows the peers need) run mid-kernel
@@ -458,6 +461,11 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
     return v;
 }
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -467,7 +475,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     return t;
 }
 // one thread per peer: spin until the peer's slot reached wait_epoch; gives up after 4 s (error flag, no hang)
-__device__ __forceinline__ void halo_wait(const HaloDev& h, int i) {
+__device__ __forceinline__ void halo_wait(const HaloDev& h, int i, bool full_fence = true) {
     const uint32_t* f = h.my_flag[i];
     if ((int32_t)(ld_relaxed_sys(f) - h.wait_epoch) < 0) {
         const uint64_t t0 = globaltimer_ns();
@@ -477,7 +485,12 @@ __device__ __forceinline__ void halo_wait(const HaloDev& h, int i) {
             __nanosleep(64);
         }
     }
-    fence_acq_rel_sys();        // the peer's rows were fenced before its flag: they are visible from here on
+    // The peer released its flag after fencing its rows.  Readers that go through L1 (the per-tile kernel's x gather, unstaged
+    // tiles) need the full fence: it also drops the SM's L1 lines (SASS CCTL.IVALL), and a 32-column line that straddles the own /
+    // halo boundary may have been cached before the peer's part of it arrived.  The streaming kernel reads x with bulk copies
+    // (L2): an acquire load of the flag pairs with the peer's st.release.sys and does not stall the warp for microseconds.
+    if (full_fence) fence_acq_rel_sys();
+    else (void)ld_acquire_sys(f);
 }
 // one thread of every pushing CTA, after the CTA's remote stores were fenced (system scope) and barriered
 __device__ __forceinline__ void halo_signal(const HaloDev& h) {
@@ -730,24 +743,18 @@ __device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volat
 
 constexpr int STREAM_DR = 8, STREAM_PD = 4;      // descriptor ring slots / prefetch distance of a producer
 
-// Multi-GPU code of the streaming kernel, kept out of line: inlined, it cost the multiply loop its register allocation (ncu, one
-// GPU acting as its own peer: 64.5 M warp instructions against 51.9 M, 82 us against 68 us) although it runs for 16 tiles of 32768.
-__device__ __noinline__ bool halo_tile_pushes(const HaloDev* hd, int t, int trow0, int trow1) {
-    bool part = t == hd->solo_tile;
-    for (int i = 0; i < hd->n_push; i++) part |= hd->lo[i] < trow1 && hd->hi[i] > trow0;
-    return part;
-}
-__device__ __noinline__ bool halo_tile_waits(const HaloDev* hd, int t, int trow0, int trow1, int nb, int lmin, int lmax) {
-    return halo_tile_pushes(hd, t, trow0, trow1) || (nb > 0 && ((int64_t)lmin * 32 < hd->own_c0 || ((int64_t)lmax + 1) * 32 > hd->own_c1));
-}
-__device__ __noinline__ void halo_wait_all(const HaloDev* hd, int lane) {
-    if (lane < hd->n_peer) halo_wait(*hd, lane);
+// The rare multi-GPU actions of the streaming kernel, out of line: a tile in 2000 waits for the peers or pushes rows, and inlined
+// these bodies (spin loops, system fences, a named barrier) cost the multiply loop its schedule.
+__device__ __noinline__ void halo_wait_all(const HaloDev* hd, int lane, bool full_fence) {
+    if (lane < hd->n_peer) halo_wait(*hd, lane, full_fence);
 }
 __device__ __noinline__ void halo_push_tile(const HaloDev* hd, int row, int rows, bool active, float a0, float a1, float a2, float a3, int gt, int bar_id, int nthreads) {
     if (active) { const float acc[4] = {a0, a1, a2, a3}; halo_store<4>(*hd, row, rows, acc); }
-    __threadfence_system();
+    // the group's remote stores happen-before its barrier, the barrier before thread 0's system fence (cumulative), the fence
+    // before the counter / flag: one fence per pushing tile instead of one per thread -- a system fence stalls its warp for
+    // microseconds, and a CTA that stalls finishes its static share of the tiles that much later than everybody else
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
-    if (gt == 0) halo_signal(*hd);
+    if (gt == 0) { __threadfence_system(); halo_signal(*hd); }
 }
 
 template <typename T, typename X, int RTT, int NG, int MINB, typename H = NoHalo>
@@ -780,6 +787,7 @@ __global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(
     // rows the peers wait for) run mid-kernel.
     auto tile_of = [&](int k) {
         int q = q0 + k * qstep;
+        if (a.tile_list) return a.tile_list[q];
         if constexpr (DIST) { q += hd.rot; if (q >= sa.ntiles) q -= sa.ntiles; }
         return a.tile0 + q;
     };
@@ -830,7 +838,6 @@ __global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(
             const uint32_t v0 = (uint32_t)d0.z, v0a = v0 & ~(uint32_t)(VA - 1);
             const bool staged = (d1.y & 1) && nb <= a.cap_blk && nv <= a.cap_val && nl <= a.cap_lines;
             const int r0 = t * RTT, nrow = min(RTT, a.nbr - r0);
-            if (round) mbar_wait(empty + s, (round - 1u) & 1u);          // the stage's previous tile has been consumed
             const uint32_t sp32 = gbase + (uint32_t)s * so.stride;
             unsigned char* sp = smem + (size_t)(g * spg + s) * so.stride;
             const uint32_t nrb = (uint32_t)((nrow + 1 + 1) & ~1) * 8;
@@ -843,23 +850,31 @@ __global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(
                 nvb = ((v0 + (uint32_t)nv - v0a + (uint32_t)(VA - 1)) & ~(uint32_t)(VA - 1)) * (uint32_t)sizeof(T);
                 nlc = (d1.y & 2) ? nl - 1 : nl;                          // a last line that reaches past the last column is loaded by hand
             }
+            bool part = false;                                            // DIST: this tile owns rows a peer needs
+            if constexpr (DIST) {
+                // A tile whose x lines leave this rank's own columns must not read x before the peers' rows are in, and a tile that
+                // pushes rows waits too (back-pressure, see spmv_tile_kernel).  The producer waits on the tile's behalf before it
+                // completes `full`; the rotated tile order puts these tiles mid-kernel, where the wait is over before it starts.
+                // Whether the tile pushes goes to the consumers through the stage header: evaluated by them, the loop over the push
+                // ranges cost every warp ~100 instructions per tile (ncu: 64.5 M warp instructions against 51.9 M).
+                part = t == hd.solo_tile;
+                for (int i = 0; i < hd.n_iv; i++) part |= t >= hd.iv_lo[i] && t <= hd.iv_hi[i];
+                if (part || (nb > 0 && ((int64_t)d1.z * 32 < hd.own_c0 || ((int64_t)d1.w + 1) * 32 > hd.own_c1))) {
+                    halo_wait_all(&hd, lane, !staged);
+                    __syncwarp();
+                }
+            }
+            // everything above is ready before the stage is: what follows the wait is the stage's critical path (a group has two
+            // stages; a microsecond between a stage's release and its next copies is a microsecond without loads in flight)
+            if (round) mbar_wait(empty + s, (round - 1u) & 1u);          // the stage's previous tile has been consumed
             if (staged && nlc < nl) {
                 const uint32_t col = (uint32_t)d1.w * 32u + (uint32_t)lane;          // lmax is the tile's last line
                 sts_x<X>(sp32 + so.xs + ((uint32_t)(nl - 1) * 32u + (uint32_t)lane) * SX, col < (uint32_t)a.cols ? x[col] : X(0.f));
                 __syncwarp();
             }
-            if constexpr (DIST) {
-                // A tile whose x lines leave this rank's own columns must not read x before the peers' rows are in, and a tile that
-                // pushes rows waits too (back-pressure, see spmv_tile_kernel).  The producer waits on the tile's behalf before it
-                // completes `full`; the rotated tile order puts these tiles mid-kernel, where the wait is over before it starts.
-                if (halo_tile_waits(&hd, t, r0 * 8, min(a.rows, (r0 + nrow) * 8), nb, d1.z, d1.w)) {
-                    halo_wait_all(&hd, lane);
-                    __syncwarp();
-                }
-            }
             const bool by_runs = d2.x > 0;
             if (lane == 0) {
-                *reinterpret_cast<int4*>(sp) = make_int4(p0, (int)v0, staged ? 1 : 0, 0);
+                *reinterpret_cast<int4*>(sp) = make_int4(p0, (int)v0, (staged ? 1 : 0) | (part ? 2 : 0), t);     // the consumers take the tile from here
                 mbar_arrive_expect_tx(full + s, n8 + n2 + nvb + nrb + (uint32_t)nlc * 32u * SX);
                 bulk_g2s(sp + so.row, a.rowpair + r0, nrb, full + s);
                 if (n8) bulk_g2s(sp + so.bm, a.bmps + p0a, n8, full + s);
@@ -894,13 +909,13 @@ __global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(
         const int lbr = gt >> 1, h = gt & 1;
         int s = 0; uint32_t par = 0;
         for (int k = 0; k < n_k; k++) {
-            const int t = tile_of(k);
-            const int r0 = t * RTT, nrow = min(RTT, a.nbr - r0);
             mbar_wait(full + s, par);
             const uint32_t sb = gbase + (uint32_t)s * so.stride;
-            const int4 hdr = lds_v4(sb);
+            const int4 hdr = lds_v4(sb);                                  // {first block, first value, staged | pushes << 1, tile}
+            const int t = hdr.w;
+            const int r0 = t * RTT, nrow = min(RTT, a.nbr - r0);
             const int p0 = hdr.x; const uint32_t v0a = (uint32_t)hdr.y & ~(uint32_t)(VA - 1);
-            const bool staged = hdr.z != 0;
+            const bool staged = (hdr.z & 1) != 0;
             const int row = (r0 + lbr) * 8 + h * 4;
             const bool active = lbr < nrow && row < a.rows;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -924,7 +939,7 @@ __global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(
                 }
             }
             if constexpr (DIST) {
-                if (halo_tile_pushes(&hd, t, r0 * 8, min(a.rows, (r0 + nrow) * 8)))
+                if (hdr.z & 2)                                           // the producer found rows of this tile in a push range
                     halo_push_tile(&hd, row, a.rows, active, acc[0], acc[1], acc[2], acc[3], gt, 1 + g, GT);
             }
             __syncwarp();
@@ -951,7 +966,7 @@ __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __re
                                                            const uint64_t* __restrict__ offsets, const T* __restrict__ values,
                                                            const int4* __restrict__ work, int n_work, int rows,
                                                            const X* __restrict__ x, float* __restrict__ y,
-                                                           float* __restrict__ partial) {
+                                                           float* __restrict__ partial, const int32_t* __restrict__ brp) {
     constexpr int UNR = 4;
     __shared__ float s_acc[8][8][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -962,6 +977,32 @@ __global__ void __launch_bounds__(256) spmv_blockpar_kernel(const uint64_t* __re
     float (*acc)[32] = s_acc[wid];
 #pragma unroll
     for (int r = 0; r < 8; r++) acc[r][lane] = 0.f;
+    if (w.w == 2) {
+        // bundle: lanes 8q .. 8q+7 take block row w.x + q, one block per lane (at most 8 per row); the eight per-row sums are
+        // reduced over the 8 lanes of the group (3 shuffle steps each) and lane 8q + r stores row r: 128 contiguous bytes per warp
+        const int sub = lane >> 3, l8 = lane & 7, br = w.x + sub;
+        const int b = __ldg(brp + br) + l8;
+        if (b < __ldg(brp + br + 1)) {
+            uint64_t rem = ld_stream_u64(bmps + b);
+            const uint32_t xb = (uint32_t)ld_stream_s32(bcol + b) * 8u;
+            uint64_t k = offsets[b];
+            while (rem) {
+                const int p = __clzll((long long)rem);
+                rem &= ~(0x8000000000000000ull >> p);
+                acc[p >> 3][lane] += val_to_f32(values[k++]) * ld_x<X>(x, xb + (uint32_t)(p & 7));
+            }
+        }
+        float res = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            float v = acc[r][lane];
+            v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+            if (l8 == r) res = v;
+        }
+        const int64_t row = (int64_t)br * 8 + l8;
+        if (row < rows) y[row] = res;
+        return;
+    }
     uint64_t vbase = w.y < w.z ? offsets[w.y] : 0;
     for (int b0 = w.y; b0 < w.z; b0 += 32 * UNR) {
         uint64_t bmp[UNR]; uint32_t xb[UNR], cnt[UNR], inc[UNR];
@@ -1049,15 +1090,32 @@ __global__ void spmv_fixup_kernel(const int32_t* __restrict__ item_ofs, const fl
     }
 }
 
-__global__ void work_count_kernel(const int32_t* __restrict__ brp, int nbr, uint32_t* __restrict__ cnt) {
+// Four consecutive block rows (an aligned group) with at most 8 blocks each form ONE work item, a "bundle" (w = 2): eight lanes per
+// block row instead of a warp.  R-MAT-22 has 4.2 M matrix rows, 52 % of them empty: a warp per block row cost 41 ns per row -- 29 %
+// of the product -- mostly its 40 reduction shuffles.
+constexpr int BUNDLE_ROWS = 4, BUNDLE_MAXB = 8;
+__device__ __forceinline__ bool is_bundle(const int32_t* __restrict__ brp, int nbr, int br) {
+    const int g0 = br & ~(BUNDLE_ROWS - 1);
+    if (g0 + BUNDLE_ROWS > nbr) return false;
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < BUNDLE_ROWS; q++) ok &= brp[g0 + q + 1] - brp[g0 + q] <= BUNDLE_MAXB;
+    return ok;
+}
+__global__ void work_count_kernel(const int32_t* __restrict__ brp, int nbr, uint32_t* __restrict__ cnt, int bundles) {
     int br = blockIdx.x * blockDim.x + threadIdx.x;
     if (br >= nbr) return;
+    if (bundles && is_bundle(brp, nbr, br)) { cnt[br] = (br & (BUNDLE_ROWS - 1)) == 0 ? 1u : 0u; return; }
     int nb = brp[br + 1] - brp[br];
     cnt[br] = nb <= SLICE ? 1u : (uint32_t)((nb + SLICE - 1) / SLICE);
 }
-__global__ void work_fill_kernel(const int32_t* __restrict__ brp, int nbr, const uint32_t* __restrict__ ofs, int4* __restrict__ work) {
+__global__ void work_fill_kernel(const int32_t* __restrict__ brp, int nbr, const uint32_t* __restrict__ ofs, int4* __restrict__ work, int bundles) {
     int br = blockIdx.x * blockDim.x + threadIdx.x;
     if (br >= nbr) return;
+    if (bundles && is_bundle(brp, nbr, br)) {
+        if ((br & (BUNDLE_ROWS - 1)) == 0) work[ofs[br]] = make_int4(br, brp[br], brp[br + BUNDLE_ROWS], 2);
+        return;
+    }
     int b0 = brp[br], b1 = brp[br + 1];
     uint32_t o = ofs[br], n = ofs[br + 1] - o;
     for (uint32_t i = 0; i < n; i++) {
@@ -1125,27 +1183,31 @@ int plan_spmv(bmsp_matrix_s* m, cudaStream_t st) {
     if (m->spmv_path == 0) return plan_tiles(m, st);
     uint32_t* cnt = nullptr;
     BMSP_TRY(dev_alloc_t(&cnt, (size_t)m->nbr + 1, st));
-    work_count_kernel<<<(unsigned)ceil_div(m->nbr, 256), 256, 0, st>>>(m->brp, m->nbr, cnt);
+    static const int bundles = env_int("BMSP_SPMV_BUNDLES", 1);
+    work_count_kernel<<<(unsigned)ceil_div(m->nbr, 256), 256, 0, st>>>(m->brp, m->nbr, cnt, bundles);
     BMSP_KERNEL_CHECK();
     BMSP_TRY(exclusive_scan_u32(cnt, cnt, m->nbr, st));
     uint32_t total = 0;
     BMSP_CUDA(cudaMemcpyAsync(&total, cnt + m->nbr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     BMSP_CUDA(cudaStreamSynchronize(st));
     m->n_work = (int32_t)total;
-    m->n_split = (int32_t)total - m->nbr;   // > 0 iff some block row is sliced
     BMSP_TRY(dev_alloc((void**)&m->work, sizeof(int4) * (size_t)total, st));
-    work_fill_kernel<<<(unsigned)ceil_div(m->nbr, 256), 256, 0, st>>>(m->brp, m->nbr, cnt, (int4*)m->work);
+    work_fill_kernel<<<(unsigned)ceil_div(m->nbr, 256), 256, 0, st>>>(m->brp, m->nbr, cnt, (int4*)m->work, bundles);
     BMSP_KERNEL_CHECK();
     m->split_rows = (int32_t*)cnt;           // item offsets per block row, kept for the fix-up
-    if (m->n_split > 0) {
-        BMSP_TRY(dev_alloc_t(&m->split_partial, (size_t)total * 8, st));
-        BMSP_TRY(dev_alloc_t(&m->split_list, (size_t)m->n_split + 1, st));      // a sliced row adds at least one item
-        int32_t* cntr = m->split_list + m->n_split;
+    // sliced block rows (more than one item): listed on the device.  (Items minus block rows no longer says whether there are any:
+    // a bundle is one item for four block rows.)  A sliced row has at least two items, so there are at most total / 2 of them.
+    {
+        const size_t cap = (size_t)total / 2 + 1;
+        BMSP_TRY(dev_alloc_t(&m->split_list, cap + 1, st));
+        int32_t* cntr = m->split_list + cap;
         BMSP_CUDA(cudaMemsetAsync(cntr, 0, sizeof(int32_t), st));
         split_list_kernel<<<(unsigned)ceil_div(m->nbr, 256), 256, 0, st>>>(m->split_rows, m->nbr, m->split_list, cntr);
         BMSP_KERNEL_CHECK();
         BMSP_CUDA(cudaMemcpyAsync(&m->n_split_rows, cntr, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         BMSP_CUDA(cudaStreamSynchronize(st));
+        m->n_split = m->n_split_rows;         // > 0 iff some block row is sliced
+        if (m->n_split > 0) BMSP_TRY(dev_alloc_t(&m->split_partial, (size_t)total * 8, st));
     }
     return BMSP_OK;
 }
@@ -1213,10 +1275,11 @@ static int launch_stream_kernel(const TileArgs<T>& a, const X* x, float* y, cons
 // tile0 / ntiles: path 0 only -- launch the tiles [tile0, tile0 + ntiles) (ntiles < 0: all of them).
 // hd: NoHalo, or HaloDev for the fused multi-GPU product (path 0, fp32 x, all tiles).
 template <typename T, typename X, typename H = NoHalo>
-static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, int tile0 = 0, int ntiles = -1, const H& hd = H()) {
+static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, int tile0 = 0, int ntiles = -1, const H& hd = H(),
+                       const int32_t* tile_list = nullptr) {
     if (A->spmv_path == 0) {
         TileArgs<T> a;
-        a.tile0 = tile0;
+        a.tile0 = tile0; a.tile_list = nullptr;
         a.bmps = A->bmps; a.bcol = A->bcol; a.values = (const T*)A->values; a.rowpair = (const int2*)A->tile_rowpair;
         a.desc = (const TileDesc*)A->tile_desc; a.lines = A->tile_lines; a.xoff = A->tile_xoff;
         a.rows = A->rows; a.nbr = A->nbr; a.cols = A->cols; a.cap_blk = A->cap_blk; a.cap_val = A->cap_val; a.cap_lines = A->cap_lines;
@@ -1225,6 +1288,7 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, 
         const size_t smem = a.so.total;
         const int grid = ntiles < 0 ? (int)ceil_div(A->nbr, rt) : ntiles;
         if (grid <= 0) return BMSP_OK;
+        a.tile_list = tile_list;
         if (A->spmv_kernel == 0) {
             // streaming kernel: one group (a producer warp + 2 * rt consumer threads) per CTA; CTAs per SM bounded by registers
             if (rt == 128) return launch_stream_kernel<T, X, 128, 1, 3, H>(a, x, y, hd, grid, st);
@@ -1241,7 +1305,7 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, 
     }
     const unsigned grid1 = (unsigned)ceil_div(A->n_work, 8), grid2 = (unsigned)ceil_div((int64_t)A->n_split_rows * 8, 256);
     spmv_blockpar_kernel<T, X><<<grid1, 256, 0, st>>>(A->bmps, A->bcol, A->offsets, (const T*)A->values, (const int4*)A->work, A->n_work,
-                                                    A->rows, x, y, A->split_partial);
+                                                    A->rows, x, y, A->split_partial, A->brp);
     BMSP_KERNEL_CHECK();
     if (A->n_split > 0) {
         spmv_fixup_kernel<<<grid2, 256, 0, st>>>(A->split_rows, A->split_partial, A->split_list, A->n_split_rows, A->rows, y);
@@ -1489,6 +1553,55 @@ extern "C" int bmsp_halo_status(const bmsp_halo_desc* halo, void* stream, int32_
     return BMSP_OK;
 }
 
+// Multi-GPU product, row-tiled path: which tiles depend on the peers (their x lines leave the rank's own columns) or push rows
+// to them.  These "boundary" tiles run first, in a small launch of the halo variant of the streaming kernel (it waits for the
+// peers' epoch, multiplies, stores the peers' rows over NVLink and publishes the next epoch -- the peers get their rows a whole
+// kernel early); the interior tiles follow in a launch of the plain kernel.  One launch of the halo variant over all tiles cost
+// 75.7 us against 67.9 us for the plain kernel on P4096 (one GPU as its own peer) although 32 of 32768 tiles do anything special.
+__global__ void halo_classify_kernel(const TileDesc* __restrict__ desc, int ntiles, int rt, int rows, int own_c0, int own_c1, int n_push,
+                                     const int* __restrict__ lo, const int* __restrict__ hi, uint32_t* __restrict__ flag) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const TileDesc d = desc[t];
+    bool b = d.nb > 0 && ((int64_t)d.lmin * 32 < own_c0 || ((int64_t)d.lmax + 1) * 32 > own_c1);
+    const int trow0 = t * rt * 8, trow1 = min(rows, (t + 1) * rt * 8);
+    for (int i = 0; i < n_push; i++) b |= lo[i] < trow1 && hi[i] > trow0;
+    flag[t] = b ? 1u : 0u;
+}
+__global__ void halo_lists_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pre, int ntiles, int32_t* __restrict__ list) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const uint32_t nb = pre[ntiles];
+    list[flag[t] ? pre[t] : nb + ((uint32_t)t - pre[t])] = t;
+}
+static int halo_classify(bmsp_matrix_s* A, const HaloDev& h, cudaStream_t st) {
+    int32_t key[18] = {h.own_c0, h.own_c1};
+    for (int i = 0; i < h.n_push; i++) { key[2 + 2 * i] = h.lo[i]; key[3 + 2 * i] = h.hi[i]; }
+    if (A->halo_n_boundary >= 0 && !memcmp(key, A->halo_key, sizeof(key))) return BMSP_OK;
+    const int ntiles = (int)ceil_div(A->nbr, A->tile_rows);
+    if (!A->halo_tiles) BMSP_TRY(dev_alloc_t(&A->halo_tiles, (size_t)ntiles + 1, st));
+    uint32_t *flag = nullptr, *pre = nullptr; int* rng = nullptr;
+    BMSP_TRY(dev_alloc_t(&flag, (size_t)ntiles + 1, st));
+    BMSP_TRY(dev_alloc_t(&pre, (size_t)ntiles + 2, st));
+    BMSP_TRY(dev_alloc_t(&rng, 2 * HALO_MAX, st));
+    BMSP_CUDA(cudaMemcpyAsync(rng, h.lo, sizeof(int) * HALO_MAX, cudaMemcpyHostToDevice, st));
+    BMSP_CUDA(cudaMemcpyAsync(rng + HALO_MAX, h.hi, sizeof(int) * HALO_MAX, cudaMemcpyHostToDevice, st));
+    halo_classify_kernel<<<(unsigned)ceil_div(ntiles, 256), 256, 0, st>>>((const TileDesc*)A->tile_desc, ntiles, A->tile_rows, A->rows, h.own_c0, h.own_c1,
+                                                                        h.n_push, rng, rng + HALO_MAX, flag);
+    BMSP_KERNEL_CHECK();
+    BMSP_TRY(exclusive_scan_u32(flag, pre, ntiles, st));
+    halo_lists_kernel<<<(unsigned)ceil_div(ntiles, 256), 256, 0, st>>>(flag, pre, ntiles, A->halo_tiles);
+    BMSP_KERNEL_CHECK();
+    uint32_t nb = 0;
+    BMSP_CUDA(cudaMemcpyAsync(&nb, pre + ntiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    BMSP_CUDA(cudaMemcpyAsync(&A->halo_first, A->halo_tiles, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    BMSP_CUDA(cudaStreamSynchronize(st));          // also: the pageable h.lo / h.hi copies above are done
+    dev_free(flag, st); dev_free(pre, st); dev_free(rng, st);
+    A->halo_n_boundary = (int32_t)nb;
+    memcpy(A->halo_key, key, sizeof(key));
+    return BMSP_OK;
+}
+
 extern "C" int bmsp_spmv_halo(bmsp_matrix_t A, const float* x_ext, float* y_own, const bmsp_halo_desc* halo, uint32_t wait_epoch,
                               uint32_t signal_epoch, void* stream) {
     if (!A || !x_ext || !y_own) { set_error("bmsp_spmv_halo: null argument"); return BMSP_ERR_INVALID; }
@@ -1503,6 +1616,8 @@ extern "C" int bmsp_spmv_halo(bmsp_matrix_t A, const float* x_ext, float* y_own,
     if (A->spmv_path < 0) BMSP_TRY(plan_spmv(A, st));
     static int fused = -1;
     if (fused < 0) { const char* e = getenv("BMSP_HALO_FUSED"); fused = e ? atoi(e) : 1; }
+    static const int fake = env_int("BMSP_HALO_FAKE", 0);      // experiment: the plain kernel behind this entry point (no exchange!)
+    if (fake) return bmsp_spmv(A, x_ext, BMSP_F32, y_own, stream);
     if (A->spmv_path == 0 && fused) {
         // tiles that own pushed rows (union of the ranges' tile intervals); they count down to the signal
         const int64_t rpt = (int64_t)A->tile_rows * 8;
@@ -1510,12 +1625,58 @@ extern "C" int bmsp_spmv_halo(bmsp_matrix_t A, const float* x_ext, float* y_own,
         for (int i = 0; i < h.n_push; i++) if (h.hi[i] > h.lo[i]) iv.push_back({h.lo[i] / rpt, (h.hi[i] - 1) / rpt});
         std::sort(iv.begin(), iv.end());
         int64_t n = 0, reach = -1;
-        for (auto& p : iv) { const int64_t a0 = std::max(p.first, reach + 1); if (p.second >= a0) { n += p.second - a0 + 1; reach = p.second; } }
+        h.n_iv = 0;
+        for (auto& p : iv) {
+            const int64_t a0 = std::max(p.first, reach + 1);
+            if (p.second >= a0) { n += p.second - a0 + 1; reach = p.second; h.iv_lo[h.n_iv] = (int32_t)a0; h.iv_hi[h.n_iv] = (int32_t)p.second; h.n_iv++; }
+        }
         if (n == 0) { h.solo_tile = 0; n = 1; }
         h.n_sig = (uint32_t)n;
         static int rotate = -1;
         if (rotate < 0) { const char* e = getenv("BMSP_HALO_ROTATE"); rotate = e ? atoi(e) : 1; }
         h.rot = rotate ? (int)(ceil_div(A->nbr, A->tile_rows) / 2) : 0;
+        static int split = -1;
+        // 0: one launch of the halo variant over all tiles (76 us on P4096, one GPU as its own peer; the plain kernel takes 68 us);
+        // 1: boundary launch, then interior launch on the same stream (85.7 us: the small launch is all latency);
+        // 2: the boundary launch on a side stream NEXT TO the interior launch
+        // (measured 79.5 us: the side-stream launch buys nothing either -- the default stays one launch)
+        if (split < 0) { const char* e = getenv("BMSP_HALO_SPLIT"); split = e ? atoi(e) : 0; }
+        const int ntiles = (int)ceil_div(A->nbr, A->tile_rows);
+        if (split && A->spmv_kernel == 0) {
+            BMSP_TRY(halo_classify(A, h, st));
+            const int nb = A->halo_n_boundary;
+            if (nb * 4 <= ntiles) {
+                // boundary tiles (the solo tile, if any, is tile 0: make sure it is among them) with the halo variant, the rest plain
+                if (h.solo_tile >= 0 && nb == 0) h.solo_tile = -2;           // nothing pushes and nothing waits: signal from a kernel of its own
+                cudaStream_t sb = st;
+                if (split == 2 && nb > 0 && ntiles > nb) {
+                    if (!A->halo_side) {
+                        BMSP_CUDA(cudaStreamCreateWithFlags(&A->halo_side, cudaStreamNonBlocking));
+                        BMSP_CUDA(cudaEventCreateWithFlags(&A->halo_fork, cudaEventDisableTiming));
+                        BMSP_CUDA(cudaEventCreateWithFlags(&A->halo_join, cudaEventDisableTiming));
+                    }
+                    sb = A->halo_side;
+                    BMSP_CUDA(cudaEventRecord(A->halo_fork, st));              // both launches read what the previous step wrote
+                    BMSP_CUDA(cudaStreamWaitEvent(sb, A->halo_fork, 0));
+                }
+                if (nb > 0) {
+                    if (h.solo_tile >= 0) h.solo_tile = A->halo_first;        // the first boundary tile signals on behalf of a rank that pushes nothing
+                    BMSP_TRY((A->dtype == BMSP_F16 ? launch_spmv<__half, float, HaloDev>(A, x_ext, y_own, sb, 0, nb, h, A->halo_tiles)
+                                                  : launch_spmv<float, float, HaloDev>(A, x_ext, y_own, sb, 0, nb, h, A->halo_tiles)));
+                    if (sb != st) BMSP_CUDA(cudaEventRecord(A->halo_join, sb));
+                } else {
+                    halo_wait_kernel<<<1, 32, 0, st>>>(h);
+                    BMSP_KERNEL_CHECK();
+                    halo_flag_kernel<<<1, 32, 0, st>>>(h);
+                    BMSP_KERNEL_CHECK();
+                }
+                if (ntiles > nb)
+                    BMSP_TRY((A->dtype == BMSP_F16 ? launch_spmv<__half, float, NoHalo>(A, x_ext, y_own, st, 0, ntiles - nb, NoHalo(), A->halo_tiles + nb)
+                                                  : launch_spmv<float, float, NoHalo>(A, x_ext, y_own, st, 0, ntiles - nb, NoHalo(), A->halo_tiles + nb)));
+                if (sb != st) BMSP_CUDA(cudaStreamWaitEvent(st, A->halo_join, 0));      // the step is complete on the caller's stream
+                return BMSP_OK;
+            }
+        }
         return A->dtype == BMSP_F16 ? launch_spmv<__half, float, HaloDev>(A, x_ext, y_own, st, 0, -1, h)
                                     : launch_spmv<float, float, HaloDev>(A, x_ext, y_own, st, 0, -1, h);
     }
