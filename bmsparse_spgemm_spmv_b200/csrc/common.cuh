@@ -41,6 +41,8 @@ struct bmsp_matrix_s {
     int32_t tile_rows = 64;     // block rows per tile (64, 32 or 16)
     int32_t spmv_kernel = 0;    // row-tiled path: 0 = streaming kernel (persistent CTAs, staged tiles in a shared-memory ring), 1 = one CTA per tile
     int32_t xl_pitch = 32;      // elements between staged x lines (32 for the streaming kernel's bulk copies, 33 for the per-tile kernel)
+    int32_t* spmv_sched = nullptr;  // streaming kernel: SCHED_SLOTS x {next tile to claim, groups done}; a launch takes the next slot
+    uint32_t spmv_sched_next = 0;
     void* tile_rowpair = nullptr;   // [nbr+1] int2 (block_row_ptr, first value) zipped for one bulk copy per tile
     void* tile_desc = nullptr;  // [ntiles] TileDesc (spmv.cu): block / value / x-line ranges of every tile of 64 block rows
     uint32_t* tile_lines = nullptr;   // [nblk] distinct x lines (32 columns) of every tile, stored from the tile's first block index

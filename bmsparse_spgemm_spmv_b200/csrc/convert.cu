@@ -42,21 +42,56 @@ __device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, in
     return lo;
 }
 
-// K1: one thread per CSR entry.  Finds its row, validates, computes its position in the block-row
-// order (block column, then row-major or column-major inside the block: block_order,
-// bmSpMatrix.cu:45-74) and scatters (key, cell position, source index) there.
-template <bool TRANSPOSED>
-__global__ void __launch_bounds__(256) rank_kernel(const int32_t* __restrict__ rp, const int32_t* __restrict__ ci, int32_t rows,
-                                                   int32_t cols, int64_t nnz, uint64_t* __restrict__ s_key,
-                                                   uint8_t* __restrict__ s_p, int32_t* __restrict__ s_src,
-                                                   int32_t* __restrict__ flags) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nnz) return;
-    // row = last r with rp[r] <= e
+// K0: the row of the first entry of every chunk of RANK_T entries (last r with rp[r] <= e), one thread per chunk.  The only
+// place that searches all of row_ptr: a search per ENTRY was 24 dependent L2 round trips on a 16 M-row matrix and two thirds of the
+// whole conversion (ncu launch list, profiles/r2_bench_launches_summary.txt).
+constexpr int RANK_T = 256, RANK_SPAN = 1024;
+__global__ void chunk_row_kernel(const int32_t* __restrict__ rp, int32_t rows, int64_t nnz, int32_t* __restrict__ chunk_row, int64_t nchunks) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nchunks) return;
+    if (b == nchunks) { chunk_row[b] = rows - 1; return; }
+    const int64_t e = b * RANK_T;
     int lo = 0, hi = rows;   // invariant: rp[lo] <= e < rp[hi]
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
         if ((int64_t)__ldg(rp + mid) <= e) lo = mid; else hi = mid;
+    }
+    chunk_row[b] = lo;
+}
+
+// K1: one thread per CSR entry, a CTA per chunk of RANK_T entries.  The chunk's rows lie between the rows of its first entry and
+// of the next chunk's first entry: their row_ptr values go to shared memory and every thread finds its row there.  It then
+// validates, computes its position in the block-row order (block column, then row-major or column-major inside the block:
+// block_order, bmSpMatrix.cu:45-74) and scatters (key, cell position, source index) there.
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(RANK_T) rank_kernel(const int32_t* __restrict__ rp, const int32_t* __restrict__ ci, int32_t rows,
+                                                      int32_t cols, int64_t nnz, const int32_t* __restrict__ chunk_row,
+                                                      uint64_t* __restrict__ s_key, uint8_t* __restrict__ s_p, int32_t* __restrict__ s_src,
+                                                      int32_t* __restrict__ flags) {
+    __shared__ int32_t srp[RANK_SPAN + 1];
+    const int r_lo = chunk_row[blockIdx.x], r_hi = chunk_row[blockIdx.x + 1];
+    const int span = r_hi - r_lo + 1;                         // rows r_lo .. r_hi; rp[r_hi + 1] is past every entry of the chunk
+    const bool in_smem = span <= RANK_SPAN;
+    if (in_smem)
+        for (int i = threadIdx.x; i <= span; i += RANK_T) srp[i] = __ldg(rp + r_lo + i);
+    __syncthreads();
+    int64_t e = (int64_t)blockIdx.x * RANK_T + threadIdx.x;
+    if (e >= nnz) return;
+    // row = last r with rp[r] <= e
+    int lo, hi;              // invariant: rp[lo] <= e < rp[hi]
+    if (in_smem) {
+        lo = 0; hi = span;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if ((int64_t)srp[mid] <= e) lo = mid; else hi = mid;
+        }
+        lo += r_lo;
+    } else {
+        lo = r_lo; hi = r_hi + 1;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if ((int64_t)__ldg(rp + mid) <= e) lo = mid; else hi = mid;
+        }
     }
     const int r = lo;
     const int c = ci[e];
@@ -186,9 +221,9 @@ static int convert_device_csr(int32_t rows, int32_t cols, int64_t nnz, const int
     touch(m, st);
     m->rows = rows; m->cols = cols; m->nnz = nnz; m->dtype = out_dtype; m->transposed = transposed;
     uint64_t* s_key = nullptr; uint8_t* s_p = nullptr; int32_t* s_src = nullptr; int32_t* flags = nullptr;
-    uint32_t* counts = nullptr;
+    uint32_t* counts = nullptr; int32_t* chunk_row = nullptr;
     int status = BMSP_OK;
-    auto cleanup = [&]() { dev_free(s_key, st); dev_free(s_p, st); dev_free(s_src, st); dev_free(flags, st); dev_free(counts, st); };
+    auto cleanup = [&]() { dev_free(s_key, st); dev_free(s_p, st); dev_free(s_src, st); dev_free(flags, st); dev_free(counts, st); dev_free(chunk_row, st); };
     auto fail = [&](int code) { cleanup(); bmsp_destroy(m); return code; };
 #define CV_TRY(x) do { status = (x); if (status != BMSP_OK) return fail(status); } while (0)
 #define CV_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return fail(cuda_fail(e__, #x, __FILE__, __LINE__)); } while (0)
@@ -209,9 +244,13 @@ static int convert_device_csr(int32_t rows, int32_t cols, int64_t nnz, const int
         CV_TRY(dev_alloc_t(&s_p, (size_t)nnz, st));
         CV_TRY(dev_alloc_t(&s_src, (size_t)nnz + 8, st));
         CV_TRY(dev_alloc_t(&counts, (size_t)tiles + 1, st));
-        unsigned grid = (unsigned)ceil_div(nnz, 256);
-        if (transposed) rank_kernel<true><<<grid, 256, 0, st>>>(rp, ci, rows, cols, nnz, s_key, s_p, s_src, flags);
-        else            rank_kernel<false><<<grid, 256, 0, st>>>(rp, ci, rows, cols, nnz, s_key, s_p, s_src, flags);
+        const int64_t nchunks = ceil_div(nnz, RANK_T);
+        CV_TRY(dev_alloc_t(&chunk_row, (size_t)nchunks + 1, st));
+        chunk_row_kernel<<<(unsigned)ceil_div(nchunks + 1, 256), 256, 0, st>>>(rp, rows, nnz, chunk_row, nchunks);
+        CV_CUDA(cudaGetLastError());
+        unsigned grid = (unsigned)nchunks;
+        if (transposed) rank_kernel<true><<<grid, RANK_T, 0, st>>>(rp, ci, rows, cols, nnz, chunk_row, s_key, s_p, s_src, flags);
+        else            rank_kernel<false><<<grid, RANK_T, 0, st>>>(rp, ci, rows, cols, nnz, chunk_row, s_key, s_p, s_src, flags);
         CV_CUDA(cudaGetLastError());
         int32_t hflags = 0;
         CV_CUDA(cudaMemcpyAsync(&hflags, flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -727,6 +727,8 @@ struct StreamArgs {
     TileArgs<T> t;
     StageLayout so;
     int32_t spg, ntiles;         // stages per group; tiles of this launch (tile0 .. tile0 + ntiles)
+    int32_t n_static;            // a group's first n_static tiles are its static share (tile slot q0 + k * qstep) ...
+    int32_t* sched;              // ... the rest it claims one at a time from sched[0]; sched[1] counts finished groups.  nullptr: all static
 };
 
 __device__ __forceinline__ int4 lds_v4(uint32_t a) {
@@ -741,6 +743,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+constexpr int SCHED_SLOTS = 16;
 constexpr int STREAM_DR = 8, STREAM_PD = 4;      // descriptor ring slots / prefetch distance of a producer
 
 // The rare multi-GPU actions of the streaming kernel, out of line: a tile in 2000 waits for the peers or pushes rows, and inlined
@@ -781,12 +784,12 @@ __global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(
     const int g = NG == 1 ? 0 : (is_producer ? warp : (warp - NG) / (GT / 32));
     const int grid = (int)gridDim.x;
     // this group's tiles: q_k = blockIdx.x + (g + k NG) * grid, k = 0 .. n_k - 1
+    // Tile slots q = 0 .. ntiles - 1 in launch order.  A group's sequence of slots: q0 + k * qstep for its static share, then slots
+    // claimed from a counter (sa.sched).  Static shares alone leave the kernel as slow as its slowest CTA: a CTA that stalled -- a
+    // system fence after pushing rows to a peer costs microseconds, a tile of a clustered matrix can be several times the average --
+    // finishes its share that much later than the rest.  With the last part of the tiles handed out on demand the others absorb it.
     const int q0 = (int)blockIdx.x + g * grid, qstep = NG * grid;
-    const int n_k = q0 < sa.ntiles ? (sa.ntiles - q0 + qstep - 1) / qstep : 0;
-    // DIST: the tile order is rotated by half the launch so that the boundary tiles (which wait for the peers' rows and produce the
-    // rows the peers wait for) run mid-kernel.
-    auto tile_of = [&](int k) {
-        int q = q0 + k * qstep;
+    auto tile_at = [&](int q) {
         if (a.tile_list) return a.tile_list[q];
         if constexpr (DIST) { q += hd.rot; if (q >= sa.ntiles) q -= sa.ntiles; }
         return a.tile0 + q;
@@ -801,39 +804,54 @@ __global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(
         // The descriptors of the next PD tiles travel global -> shared with cp.async (no register is waited on), one commit group
         // per tile; group k is complete once at most PD newer groups are pending.
         const uint32_t ring = sbase + (uint32_t)nstage * (so.stride + 16u) + (uint32_t)g * (DR * 64u);
-        if (lane == 0) {
-            auto prefetch = [&](int k) {
-                if (k < n_k) {
-                    const char* src = reinterpret_cast<const char*>(a.desc + tile_of(k));
-                    const uint32_t dst = ring + (uint32_t)(k % DR) * 64u;
+        static_assert(NG * DR * 4 <= 64, "tile ids of the ring live in the 64 spare bytes behind it");
+        const uint32_t tq = sbase + (uint32_t)nstage * (so.stride + 16u) + (uint32_t)NG * (DR * 64u) + (uint32_t)g * (DR * 4u);
+        const int n_static = sa.sched ? sa.n_static : 0x7fffffff;
+        const int dyn_base = sa.sched ? sa.n_static * qstep : 0;
+        int pending = 0;                  // lane 0: the slot claimed for the next dynamic sequence number, asked for one iteration ahead
+        bool ended = false;               // lane 0: a slot past the last tile has been seen (every later one is past it too)
+        // descriptor of sequence number k (slot q) -> ring, its tile id -> tq; a slot past the end leaves the end marker (-1)
+        auto issue = [&](int k, int q) {
+            int t = -1;
+            if (q < sa.ntiles) {
+                t = tile_at(q);
+                const char* src = reinterpret_cast<const char*>(a.desc + t);
+                const uint32_t dst = ring + (uint32_t)(k % DR) * 64u;
 #pragma unroll
-                    for (int c = 0; c < 4; c++) cp_async16(dst + 16u * c, src + 16 * c);
-                }
-                cp_async_commit();
-            };
-            for (int k = 0; k < PD; k++) prefetch(k);
+                for (int c = 0; c < 4; c++) cp_async16(dst + 16u * c, src + 16 * c);
+            } else ended = true;
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(tq + (uint32_t)(k % DR) * 4u), "r"(t) : "memory");
+            cp_async_commit();
+        };
+        if (lane == 0) {
+            for (int k = 0; k < PD; k++) issue(k, k < n_static ? q0 + k * qstep : (ended ? sa.ntiles : dyn_base + atomicAdd(sa.sched, 1)));
+            if (PD >= n_static && !ended) pending = dyn_base + atomicAdd(sa.sched, 1);
         }
         int s = 0; uint32_t round = 0;
-        for (int k = 0; k < n_k; k++) {
+        for (int k = 0;; k++) {
             int4 d0, d1, d2, d3;
             if (lane == 0) {
-                // refill the ring, then make sure tile k's descriptor has landed
-                {
-                    const int kk = k + PD;
-                    if (kk < n_k) {
-                        const char* src = reinterpret_cast<const char*>(a.desc + tile_of(kk));
-                        const uint32_t dst = ring + (uint32_t)(kk % DR) * 64u;
-#pragma unroll
-                        for (int c = 0; c < 4; c++) cp_async16(dst + 16u * c, src + 16 * c);
-                    }
-                    cp_async_commit();
-                }
+                // refill the ring, then make sure tile k's descriptor has landed.  The claim for the sequence number after this one
+                // goes out now and is looked at in the next iteration: the atomic's round trip never stalls the warp.
+                const int kk = k + PD;
+                const int q = kk < n_static ? q0 + kk * qstep : (ended ? sa.ntiles : pending);
+                issue(kk, q);
+                if (kk + 1 >= n_static && !ended) pending = dyn_base + atomicAdd(sa.sched, 1);
                 cp_async_wait<PD>();
             }
             __syncwarp();
+            const int t = (int)lds_u32(tq + (uint32_t)(k % DR) * 4u);
+            if (t < 0) {
+                // no more tiles: tell the consumers through the next stage's header
+                if (round) mbar_wait(empty + s, (round - 1u) & 1u);
+                if (lane == 0) {
+                    *reinterpret_cast<int4*>(smem + (size_t)(g * spg + s) * so.stride) = make_int4(0, 0, 0, -1);
+                    mbar_arrive(full + s);
+                }
+                break;
+            }
             const uint32_t dsl = ring + (uint32_t)(k % DR) * 64u;
             d0 = lds_v4(dsl); d1 = lds_v4(dsl + 16); d2 = lds_v4(dsl + 32); d3 = lds_v4(dsl + 48);
-            const int t = tile_of(k);
             const int p0 = d0.x, nb = d0.y, nv = d0.w, nl = d1.x;
             const uint32_t v0 = (uint32_t)d0.z, v0a = v0 & ~(uint32_t)(VA - 1);
             const bool staged = (d1.y & 1) && nb <= a.cap_blk && nv <= a.cap_val && nl <= a.cap_lines;
@@ -903,16 +921,22 @@ __global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(
             }
             if (++s == spg) { s = 0; round++; }
         }
+        if (sa.sched && lane == 0) {
+            // the last group to finish claiming re-arms the counters for the next launch that takes this slot
+            __threadfence();
+            if (atomicAdd(sa.sched + 1, 1) == NG * grid - 1) { sa.sched[0] = 0; sa.sched[1] = 0; }
+        }
     } else {
         // ------------------------------------------------------------------------------------------ consumers
         const int gt = tid - NG * 32 - g * GT;
         const int lbr = gt >> 1, h = gt & 1;
         int s = 0; uint32_t par = 0;
-        for (int k = 0; k < n_k; k++) {
+        for (;;) {
             mbar_wait(full + s, par);
             const uint32_t sb = gbase + (uint32_t)s * so.stride;
             const int4 hdr = lds_v4(sb);                                  // {first block, first value, staged | pushes << 1, tile}
             const int t = hdr.w;
+            if (t < 0) break;                                             // the producer ran out of tiles
             const int r0 = t * RTT, nrow = min(RTT, a.nbr - r0);
             const int p0 = hdr.x; const uint32_t v0a = (uint32_t)hdr.y & ~(uint32_t)(VA - 1);
             const bool staged = (hdr.z & 1) != 0;
@@ -1230,7 +1254,7 @@ static int launch_tile_kernel(const TileArgs<T>& a, const X* x, float* y, const 
 // rest: as many CTAs per SM as fit with two stages each (a group needs a second stage to have its next tile arriving while it
 // multiplies the current one; P4096: 7 CTAs x 2 stages of 15.4 KB -- the measured optimum).
 template <typename T, typename X, int RTT, int NG, int MAXB, typename H>
-static int launch_stream_kernel(const TileArgs<T>& a, const X* x, float* y, const H& hd, int ntiles, cudaStream_t st) {
+static int launch_stream_kernel(const TileArgs<T>& a, const X* x, float* y, const H& hd, int ntiles, cudaStream_t st, int32_t* sched = nullptr) {
     auto kern = spmv_stream_kernel<T, X, RTT, NG, MAXB, H>;
     static int sms = 0;
     static size_t smem_max = 0;
@@ -1267,6 +1291,11 @@ static int launch_stream_kernel(const TileArgs<T>& a, const X* x, float* y, cons
         configured = std::max<size_t>(smem, 1);
     }
     const int grid = std::max(1, std::min((int)ceil_div(ntiles, NG), sms * ctas));
+    // the last BMSP_SPMV_DYN percent of every group's share are claimed at run time (0: static shares, 100: every tile is claimed)
+    static const int dyn_pct = std::min(100, std::max(0, env_int("BMSP_SPMV_DYN", 25)));
+    const int share = ntiles / (grid * NG);
+    sa.sched = (sched && dyn_pct > 0 && share >= 2) ? sched : nullptr;
+    sa.n_static = sa.sched ? (int)((int64_t)share * (100 - dyn_pct) / 100) : 0;
     kern<<<(unsigned)grid, NG * (32 + RTT * 2), smem, st>>>(sa, x, y, hd);
     BMSP_KERNEL_CHECK();
     return BMSP_OK;
@@ -1290,11 +1319,21 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, 
         if (grid <= 0) return BMSP_OK;
         a.tile_list = tile_list;
         if (A->spmv_kernel == 0) {
-            // streaming kernel: one group (a producer warp + 2 * rt consumer threads) per CTA; CTAs per SM bounded by registers
-            if (rt == 128) return launch_stream_kernel<T, X, 128, 1, 3, H>(a, x, y, hd, grid, st);
-            if (rt == 32) return launch_stream_kernel<T, X, 32, 1, 8, H>(a, x, y, hd, grid, st);
-            if (rt == 16) return launch_stream_kernel<T, X, 16, 1, 8, H>(a, x, y, hd, grid, st);
-            return launch_stream_kernel<T, X, 64, 1, 7, H>(a, x, y, hd, grid, st);
+            // streaming kernel: one group (a producer warp + 2 * rt consumer threads) per CTA; CTAs per SM bounded by registers.
+            // A launch over all tiles takes one of the matrix's scheduler slots in turn (launches on different streams may overlap:
+            // they must not share a counter); launches over a tile range (the host-buffer pipeline's chunks) keep static shares.
+            int32_t* sched = nullptr;
+            if (ntiles < 0 && tile_list == nullptr) {
+                if (!A->spmv_sched) {
+                    BMSP_TRY(dev_alloc_t(&A->spmv_sched, (size_t)SCHED_SLOTS * 2, st));
+                    BMSP_CUDA(cudaMemsetAsync(A->spmv_sched, 0, sizeof(int32_t) * SCHED_SLOTS * 2, st));
+                }
+                sched = A->spmv_sched + 2 * (A->spmv_sched_next++ % SCHED_SLOTS);
+            }
+            if (rt == 128) return launch_stream_kernel<T, X, 128, 1, 3, H>(a, x, y, hd, grid, st, sched);
+            if (rt == 32) return launch_stream_kernel<T, X, 32, 1, 8, H>(a, x, y, hd, grid, st, sched);
+            if (rt == 16) return launch_stream_kernel<T, X, 16, 1, 8, H>(a, x, y, hd, grid, st, sched);
+            return launch_stream_kernel<T, X, 64, 1, 7, H>(a, x, y, hd, grid, st, sched);
         }
         // default: one thread per bitmap half; BMSP_SPMV_VARIANT=1: one thread per block row (64-row tiles only).
         // Measured on P4096: 92.7 us vs 103.5 us (fewer instructions, but too few warps to hide the staging latency).

@@ -73,6 +73,32 @@ def test_long_block_row_is_sliced(B, oracle):
     _spmv_check(B, oracle, 24, nc, rp, ci, v, rng.uniform(-1, 1, nc).astype(np.float32))
 
 
+@pytest.mark.parametrize("nbr", [4, 7, 64, 1001, 4099])
+def test_block_parallel_bundles_of_short_block_rows(B, oracle, nbr):
+    """scattered single entries (fewer than 2.5 per block: the block-parallel path).  Block rows with 0 .. 9 blocks next to each
+    other exercise the bundles -- four consecutive block rows of at most 8 blocks share one warp item -- and their boundaries: a
+    block row of 9 blocks breaks its group of four, a block-row count that is no multiple of four leaves a ragged tail, and a long
+    row in the middle is still sliced."""
+    rng = np.random.default_rng(100 + nbr)
+    nr, nc = nbr * 8 - 3, 1 << 15
+    pattern = [0, 3, 8, 9, 1, 8, 8, 8, 0, 0, 0, 0, 2, 5, 7, 8]
+    rows, cols = [], []
+    for br in range(nbr):
+        k = 700 if (nbr > 64 and br == nbr // 2) else pattern[(br + br // 16) % 16]
+        bc = np.sort(rng.choice(nc // 8, k, replace=False))
+        for c in bc:                                   # one or two entries per 8x8 block
+            for _ in range(1 + int(rng.integers(0, 2))):
+                r = br * 8 + int(rng.integers(0, 8))
+                if r < nr:
+                    rows.append(r); cols.append(int(c) * 8 + int(rng.integers(0, 8)))
+    rc = np.unique(np.stack([rows, cols], 1), axis=0) if rows else np.zeros((0, 2), np.int64)
+    r, c = rc[:, 0], rc[:, 1]
+    v = rng.uniform(-1, 1, r.size).astype(np.float16).astype(np.float32)
+    rp = np.zeros(nr + 1, np.int64); np.cumsum(np.bincount(r, minlength=nr), out=rp[1:])
+    M = _spmv_check(B, oracle, nr, nc, rp.astype(np.int32), c.astype(np.int32), v, rng.uniform(-1, 1, nc).astype(np.float32))
+    assert M.nnz / max(M.block_num, 1) < 2.5
+
+
 def test_tile_overflow_falls_back_to_global(B, oracle):
     """dense-ish blocks but one tile far above the average: the row-tiled kernel must read it from global"""
     rng = np.random.default_rng(5)

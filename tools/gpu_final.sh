@@ -9,6 +9,11 @@ if [ "$N" = "1" ]; then
   python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.log 2>&1; tail -1 gpurun_out/final_smoke.log
   ( time python bench.py --steps 200 --warmup 20 ) > gpurun_out/final_bench_n1.json 2> gpurun_out/final_bench_n1.err; echo "bench rc=$?"
   python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/final_bench_n1_ref.json 2>> gpurun_out/final_bench_n1.err
+  # profiler passes (numbers printed under ncu are never bench values): launch list of the bench command, full capture of the SpMV kernel
+  # and of the conversion kernels
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/final_launches.csv python bench.py --steps 20 --warmup 5 --no-strong --no-cpu --no-spgemm > gpurun_out/final_ncu_bench.log 2>&1
+  timeout 300 ncu --set full --import-source on --clock-control none -k regex:spmv_stream_kernel -c 1 -f -o gpurun_out/final_stream python tools/spmv_bench.py p4096 3 > gpurun_out/final_ncu_stream.log 2>&1
+  timeout 300 ncu --set full --clock-control none -k regex:"chunk_row_kernel|rank_kernel|head_count_kernel|emit_kernel|values_kernel|derive_|check_rowptr" -c 8 -f -o gpurun_out/final_convert python tools/spmv_bench.py p4096 1 > gpurun_out/final_ncu_convert.log 2>&1
 else
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
   if [ "$N" -le 4 ]; then timeout 900 python -m pytest tests/test_gpu_dist.py -x -q > gpurun_out/final_pytest_n$N.log 2>&1; tail -3 gpurun_out/final_pytest_n$N.log; fi
