@@ -13,7 +13,11 @@ namespace bmsp {
 // (row pointers, y); the block-parallel kernel spends a whole warp on every block row, worth about 20 blocks of streaming
 // (fitted on the R-MAT-22 shards of a 2-GPU run, round 2: 7.9 us per 10^6 blocks + 41 us per 10^6 matrix rows with a warp per block
 // row; 23 us per 10^6 rows since short block rows are bundled four to a warp, i.e. a block row costs as much as ~330 bytes of
-// streaming).
+// streaming).  On that path every rank also stores its finished rows to every peer after the product (an all-gather written by
+// the owner), and the step ends when the rank with the MOST rows has pushed them: 32 bytes per block row and peer at the ~750 GB/s
+// a rank's NVLink egress sustains = 0.043 us per 10^6 block rows and peer = 76 byte units.  Without that term the rank that got the
+// light tail of an R-MAT matrix (1.4 M of 4.2 M rows at 8 GPUs) pushed 40 MB per step while the others waited (round 2, N = 8:
+// products of 75-103 us, steps of 161 us).
 __global__ void spmv_weight_kernel(const int32_t* __restrict__ brp, const uint32_t* __restrict__ rvb, int nbr, int vsize,
                                    uint64_t row_cost, uint64_t* __restrict__ w) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,7 +66,7 @@ extern "C" int bmsp_partition_block_rows(bmsp_matrix_t A, bmsp_matrix_t Bt, int3
     if (weight_spgemm) cand_weight_kernel<<<(unsigned)ceil_div(nbr, 8), 256, 0, st>>>(A->brp, A->bcol, Bt->brp, nbr, w);
     else {
         const bool blockpar = A->nblk > 0 && (double)A->nnz / (double)A->nblk < 2.5;      // same rule as plan_spmv
-        spmv_weight_kernel<<<(unsigned)ceil_div(nbr, 256), 256, 0, st>>>(A->brp, A->rvb, nbr, A->dtype == BMSP_F16 ? 2 : 4, blockpar ? 330 : 40, w);
+        spmv_weight_kernel<<<(unsigned)ceil_div(nbr, 256), 256, 0, st>>>(A->brp, A->rvb, nbr, A->dtype == BMSP_F16 ? 2 : 4, blockpar ? 330 + 76 * (uint64_t)(nparts - 1) : 40, w);
     }
     BMSP_KERNEL_CHECK();
     BMSP_TRY(exclusive_scan_u64(w, w, nbr, st));

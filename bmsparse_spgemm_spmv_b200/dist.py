@@ -148,6 +148,56 @@ class ShardedSpMV:
         return self.own_slice(self.x[self.cur])
 
 
+def balanced_block_row_bounds(A, group=None, iters: int = 5, reps: int = 20, push_gbps: float = 750.0, tol: float = 1.015):
+    """Block-row split of a scattered matrix (block-parallel SpMV path: every rank needs all of x) by MEASURED cost.
+
+    The model split (bmsp_partition_block_rows: blocks + block rows + the bytes a rank pushes to its peers) is only a start: on a
+    power-law matrix the cost of a block depends on where its row and column sit (hub rows gather x from everywhere, tail rows from
+    the few hub columns that stay in L1), +-15 % between shards with the same counts.  Every rank holds the whole matrix here, so it
+    slices ITS shard, times the local product, adds the time its pushes take (rows x 4 bytes x (N - 1) peers at the egress rate), the
+    ranks exchange the totals, every block row's weight in a shard is scaled by that shard's total / mean, and the split is redone.
+    Collective; returns int64 bounds[N + 1] in block rows, identical on every rank.  Setup cost: `iters` x (slice + plan + reps products).
+    """
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nb = np.diff(A.block_row_ptr.cpu().numpy().astype(np.int64))
+    nbr = len(nb)
+    w = (14.0 * nb + 330.0 + 76.0 * (world - 1))                     # the C partitioner's model for this path (dist.cu)
+    x = torch.ones(A.num_cols, dtype=torch.float32, device=dev)
+    bounds = split_by_weight(w, world)
+    best, best_max = bounds, float("inf")
+    for it in range(iters):
+        b0, b1 = int(bounds[rank]), int(bounds[rank + 1])
+        t_local = 0.0
+        if b1 > b0:
+            S = A.slice_block_rows(b0, b1, rebase=True)
+            y = torch.empty(S.num_rows, dtype=torch.float32, device=dev)
+            from .ops import bmSparse_SpMV
+            for _ in range(3):
+                bmSparse_SpMV(S, x, y)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                bmSparse_SpMV(S, x, y)
+            e1.record(); e1.synchronize()
+            t_local = e0.elapsed_time(e1) / reps * 1e3                 # us
+            del S, y
+        push = (b1 - b0) * 32.0 * (world - 1) / (push_gbps * 1e3)       # us: 32 bytes per block row and peer
+        mine = torch.tensor([t_local + push], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allt, mine, group=group)
+        tot = np.array([float(t.item()) for t in allt])
+        mean = float(tot.mean())
+        if float(tot.max()) < best_max:
+            best, best_max = bounds, float(tot.max())                  # the split returned is always one that was measured
+        if mean <= 0 or float(tot.max()) <= tol * mean or it == iters - 1:
+            break
+        for p in range(world):
+            w[int(bounds[p]):int(bounds[p + 1])] *= max(0.5, min(2.0, tot[p] / mean))
+        bounds = split_by_weight(w, world)
+    return best
+
+
 def halo_descriptor(buf, rank, send, peers, own_lo, own_hi, ext_lo, my_base, peer_base, peer_layout, scratch_ptr, inbox=1024):
     """bmsp_halo_desc of x buffer `buf` for one rank (pure address arithmetic: the CPU tests check it without a GPU).
     send: [(peer, a, e)] global row ranges of mine a peer needs; peers: everybody I exchange epochs with (both directions);

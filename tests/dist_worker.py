@@ -11,7 +11,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bmsparse_spgemm_spmv_b200 as B  # noqa: E402
-from bmsparse_spgemm_spmv_b200.dist import ShardedSpMV, csr_row_slice, split_by_weight  # noqa: E402
+from bmsparse_spgemm_spmv_b200.dist import ShardedSpMV, balanced_block_row_bounds, csr_row_slice, split_by_weight  # noqa: E402
 
 G = B.generators
 
@@ -29,8 +29,19 @@ def main():
             v = (v * 0.01).astype(np.float16).astype(np.float32)
         if name in ("uniform", "clustered"):
             v = (v * 0.1).astype(np.float16).astype(np.float32)
-        w = np.add.reduceat(np.diff(rp).astype(np.float64), np.arange(0, n, 8)) + 1.0
-        bounds = split_by_weight(w, world) * 8
+        if name == "rmat":
+            # the measured-cost split of a scattered matrix: a valid partition, the same on every rank
+            Aw = B.bmSpMatrix.from_csr(n, n, rp, ci, v)
+            bb = balanced_block_row_bounds(Aw, iters=2, reps=3)
+            assert bb[0] == 0 and bb[-1] == (n + 7) // 8 and np.all(np.diff(bb) >= 0)
+            t = torch.from_numpy(np.asarray(bb, np.int64)).to(dev); t0 = t.clone()
+            dist.broadcast(t0, 0)
+            assert torch.equal(t, t0), "measured-cost bounds differ between ranks"
+            bounds = np.asarray(bb, np.int64) * 8
+            del Aw
+        else:
+            w = np.add.reduceat(np.diff(rp).astype(np.float64), np.arange(0, n, 8)) + 1.0
+            bounds = split_by_weight(w, world) * 8
         bounds[-1] = n
         lcsr = csr_row_slice(rp, ci, v, int(bounds[rank]), int(bounds[rank + 1]))
         x0 = G.x_vector(n)

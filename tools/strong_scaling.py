@@ -72,7 +72,12 @@ def sharded_spmv(c: Ctx, A, n, rp, ci, v, x0, steps, halo="auto", diagnostics=Fa
         x = d(x0); y = torch.empty(n, device=c.dev)
         ms = time_steps(c, lambda: B.bmSparse_SpMV(A, x, y), steps)
         return ms, {"halo": "none"}
-    bounds = A.partition_block_rows(c.world).astype(np.int64) * 8
+    if A.nnz < 2.5 * A.block_num:
+        # scattered matrix: split by measured cost (local product + the all-gather pushes), three rounds at set-up time
+        from bmsparse_spgemm_spmv_b200.dist import balanced_block_row_bounds
+        bounds = balanced_block_row_bounds(A).astype(np.int64) * 8
+    else:
+        bounds = A.partition_block_rows(c.world).astype(np.int64) * 8
     bounds[-1] = n
     lcsr = csr_row_slice(rp, ci, v, int(bounds[c.rank]), int(bounds[c.rank + 1]))
     sh = ShardedSpMV(bounds, lcsr, n, device=c.dev, halo=halo)
