@@ -221,9 +221,17 @@ struct RowCtx {
 };
 
 // index of the row of a work item that owns v, given the rows' ascending start offsets (A blocks, bit-set words or C blocks)
+// (nr <= 32.  Five fixed halving steps: the linear scan this replaces was 15 % of the NUMERIC pass's instructions on P4096 -- every
+// lane of every surviving pair walks the 16 rows of its group, and the lanes of a warp stop at different rows.)
 __device__ __forceinline__ int local_row(const int* bounds, int nr, int v) {
     int rl = 0;
-    while (rl + 1 < nr && v >= bounds[rl + 1]) rl++;
+    if (nr > 1) {
+#pragma unroll
+        for (int s = 16; s; s >>= 1) {
+            const int t = rl + s;
+            if (t < nr && v >= bounds[t]) rl = t;
+        }
+    }
     return rl;
 }
 
@@ -247,7 +255,7 @@ __device__ __forceinline__ float inline_val(const uint4& v, int k) {
 }
 
 template <int MODE>
-__device__ __forceinline__ void apply_pair(const GemmArgs& g, const RowCtx& r, int a, const PairIn& in, int arow = -1) {
+__device__ __forceinline__ void apply_pair(const GemmArgs& g, const RowCtx& r, int a, const PairIn& in, int arow = -1, int rpl = 1) {
     const uint4 pm = in.pm;
     const uint64_t abmp = in.abmp, bbmp = ((uint64_t)pm.y << 32) | pm.x;
     const int rl = local_row(r.abr, r.nr, a);
@@ -269,9 +277,10 @@ __device__ __forceinline__ void apply_pair(const GemmArgs& g, const RowCtx& r, i
         else { cb = g.c_bmps[r.c0 + c]; dst = g.c_val + g.c_off[r.c0 + c]; }
         uint64_t rem = abmp;
         int ka = 0;
-        if (arow >= 0) {                                    // this lane's row of the A block only
-            rem = abmp & (0xFF00000000000000ull >> (8 * arow));
-            ka = arow ? __popcll(abmp >> (64 - 8 * arow)) : 0;
+        if (arow >= 0) {                                    // this lane's rows of the A block only: rows arow * rpl .. + rpl - 1
+            const int sh = 8 * rpl * arow;
+            rem = abmp & ((~0ull << (64 - 8 * rpl)) >> sh);
+            ka = sh ? __popcll(abmp >> (64 - sh)) : 0;
             if (!rem) return;
         }
         while (rem) {
@@ -292,8 +301,8 @@ __device__ __forceinline__ void apply_pair(const GemmArgs& g, const RowCtx& r, i
 }
 
 template <int MODE>
-__device__ __forceinline__ void process_pair(const GemmArgs& g, const RowCtx& r, int a, int b, int arow = -1) {
-    apply_pair<MODE>(g, r, a, load_pair<MODE>(g, a, b), arow);
+__device__ __forceinline__ void process_pair(const GemmArgs& g, const RowCtx& r, int a, int b, int arow = -1, int rpl = 1) {
+    apply_pair<MODE>(g, r, a, load_pair<MODE>(g, a, b), arow, rpl);
 }
 
 // ---- tensor-core path (dense blocks) -----------------------------------------------------------------
@@ -862,8 +871,12 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
                 uint32_t ns = 0;
                 enumerate_fine<2, false>(g, r, ns);
             } else if (PASS == PASS_NUMERIC) {
-                if (g.split8) {
+                if (g.split8 == 8) {
                     for (uint64_t e = tid; e < (uint64_t)nsurv * 8u; e += T) { const uint2 pr = list[e >> 3]; process_pair<MODE_NUMERIC>(g, r, (int)pr.x, (int)pr.y, (int)(e & 7u)); }
+                } else if (g.split8 == 4) {             // four lanes per pair, two rows of the A block each
+                    for (uint64_t e = tid; e < (uint64_t)nsurv * 4u; e += T) { const uint2 pr = list[e >> 2]; process_pair<MODE_NUMERIC>(g, r, (int)pr.x, (int)pr.y, (int)(e & 3u), 2); }
+                } else if (g.split8 == 2) {
+                    for (uint64_t e = tid; e < (uint64_t)nsurv * 2u; e += T) { const uint2 pr = list[e >> 1]; process_pair<MODE_NUMERIC>(g, r, (int)pr.x, (int)pr.y, (int)(e & 1u), 4); }
                 } else if (MAXT == 1024) {            // 32 registers per thread: one pair at a time
                     for (uint32_t e = tid; e < nsurv; e += T) { const uint2 pr = list[e]; process_pair<MODE_NUMERIC>(g, r, (int)pr.x, (int)pr.y); }
                 } else {
@@ -1230,7 +1243,7 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     // leaves the SM at 32 one-warp CTAs, each waiting on its own chain of dependent loads (P4096 A*A: 21.7 ms, cuSPARSE 13.0 ms)
     int group = 1;
     if (avg_cand <= 96 && !sp.active && (int64_t)16 * max_words <= 8192) group = 16;
-    if (const char* e = getenv("BMSP_SPGEMM_GROUP")) { const int v = atoi(e); if (v >= 1 && v <= 32 && !sp.active && (int64_t)v * max_words <= 8192) group = v; }
+    if (const char* e = getenv("BMSP_SPGEMM_GROUP")) { const int v = atoi(e); if (v >= 1 && v <= 16 && !sp.active && (int64_t)v * max_words <= 8192) group = v; }
     int T = group > 1 ? 128 : (avg_cand <= 96 ? 32 : (avg_cand <= 2048 ? 128 : 256));
     if (G > T) G = T;
 
@@ -1295,7 +1308,8 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     g.rowinfo = rowinfo; g.row_begin = rb; g.row_end = re; g.G = G;
     // P4096 A*A: 2.1 M block rows of 25 candidate pairs -- one atomic on the queue head per row and pass cost more than the rows
     g.group = group;
-    g.split8 = A->nblk > 0 && (double)A->nnz / (double)A->nblk >= 4.0;
+    static const int split_env = [] { const char* e = getenv("BMSP_SPGEMM_SPLIT"); const int v = e ? atoi(e) : 8; return (v == 2 || v == 4 || v == 8) ? v : 8; }();
+    g.split8 = (A->nblk > 0 && (double)A->nnz / (double)A->nblk >= 4.0) ? split_env : 0;
     g.batch = group > 1 ? 2 : (avg_cand <= 96 ? 32 : (avg_cand <= 2048 ? 4 : 1));
     g.cap_words = (int64_t)group * max_words <= 8192 ? std::max(1, group * max_words) : (avg_words > 4096.0 ? 256 : 8192);
     g.cap_c = 0; g.cap_nnz = 0;
