@@ -97,7 +97,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((time.perf_counter(), mhz, r))
             except Exception:
                 pass
-            time.sleep(0.0005)
+            time.sleep(0.002)          # ~7 samples in a 14 ms timed region; a tighter poll competes with the launching thread
 
     def summary(self, t0, t1):
         inside = [s for s in self.samples if t0 <= s[0] <= t1]

@@ -111,22 +111,24 @@ def rmat_spgemm(c: Ctx, A, Bt, rp, ci, chunk_pairs=3e9, max_chunks=0):
     cand_total = int(blen[bcol].sum())
     cpr = max(1, int(np.ceil(cand_total / c.world / chunk_pairs)))
     bounds = A.partition_block_rows(c.world * cpr, Bt)
-    # block-cyclic: rank r multiplies chunks r, r + N, r + 2N, ... -- the hub rows sit in the first chunks, and a hub chunk costs
-    # more per candidate pair than a tail chunk, so contiguous ranges would leave rank 0 with the slowest ones
-    mine = range(c.rank, c.world * cpr, c.world)
+    # chunks dealt in rounds of N, every other round in reverse rank order: the hub rows sit in the first chunks and a hub chunk costs
+    # more per candidate pair than a tail chunk, so contiguous ranges would leave rank 0 with the slowest ones, and a plain cyclic deal
+    # still hands rank 0 the heavier chunk of every round
+    mine = [rnd * c.world + (c.rank if rnd % 2 == 0 else c.world - 1 - c.rank) for rnd in range(cpr)]
     c.barrier()
     spent = 0.0; blocks = 0; nnz = 0; keysum = 0; valsum = 0.0; cand = 0; surv = 0; done = 0; err = None
     for ch in mine:
         r0, r1 = int(bounds[ch]), int(bounds[ch + 1])
         if r1 <= r0:
             continue
-        torch.cuda.synchronize(); t = time.perf_counter()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
         try:
             C, info = B.bmSparse_mult(A, Bt, None, 0, False, 5, brow_range=(r0, r1))
         except B.BmspError as e:
             err = f"rows [{r0},{r1}): {e}"
             break
-        torch.cuda.synchronize(); spent += time.perf_counter() - t
+        e1.record(); e1.synchronize(); spent += e0.elapsed_time(e1) * 1e-3          # device time of the call (it syncs internally)
         blocks += C.block_num; nnz += C.nnz; cand += info.candidate_pairs; surv += info.surviving_pairs
         if C.block_num:
             keysum = (keysum + int(C.keys.sum().item())) & ((1 << 62) - 1)
@@ -136,6 +138,10 @@ def rmat_spgemm(c: Ctx, A, Bt, rp, ci, chunk_pairs=3e9, max_chunks=0):
         if max_chunks and done >= max_chunks:
             break
     ms = c.allmax(spent * 1e3)
+    per_rank_s = [round(spent, 3)]
+    if c.world > 1:
+        per_rank_s = [None] * c.world
+        c.dist.all_gather_object(per_rank_s, round(spent, 3))
     tot = c.allsum([blocks, nnz, cand, surv, done], torch.int64)
     ks = c.allsum([keysum], torch.int64)[0] & ((1 << 62) - 1)
     vs = c.allsum([valsum])[0]
@@ -146,7 +152,7 @@ def rmat_spgemm(c: Ctx, A, Bt, rp, ci, chunk_pairs=3e9, max_chunks=0):
     complete = not any(errs) and not max_chunks
     return {"value": (flops / ms / 1e6) if complete else None, "unit": "GFLOP/s incl. symbolic", "ms": ms, "flops": flops, "candidate_pairs_total": cand_total,
             "chunks_per_rank": cpr, "chunks_done": tot[4], "c_blocks": tot[0], "c_nnz": tot[1], "surviving_pairs": tot[3], "checksum_keys": ks,
-            "checksum_values": vs, "errors": [e for e in errs if e],
+            "checksum_values": vs, "errors": [e for e in errs if e], "per_rank_s": per_rank_s,
             "c_handling": "every chunk's C reduced to (blocks, values, sum of keys, sum of values) and dropped; the sums are independent of N"}
 
 
