@@ -1667,8 +1667,6 @@ extern "C" int bmsp_spmv_halo(bmsp_matrix_t A, const float* x_ext, float* y_own,
     if (A->spmv_path < 0) BMSP_TRY(plan_spmv(A, st));
     static int fused = -1;
     if (fused < 0) { const char* e = getenv("BMSP_HALO_FUSED"); fused = e ? atoi(e) : 1; }
-    static const int fake = env_int("BMSP_HALO_FAKE", 0);      // experiment: the plain kernel behind this entry point (no exchange!)
-    if (fake) return bmsp_spmv(A, x_ext, BMSP_F32, y_own, stream);
     if (A->spmv_path == 0 && fused) {
         // tiles that own pushed rows (union of the ranges' tile intervals); they count down to the signal
         const int64_t rpt = (int64_t)A->tile_rows * 8;
