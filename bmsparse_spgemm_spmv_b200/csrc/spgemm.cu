@@ -46,6 +46,8 @@ struct GemmArgs {
     const int32_t* row_list;   // when set: the rows to process, in this order (heavy-row / light-row launches); else row_begin + i
     int32_t n_list;
     int32_t batch;             // work items a CTA takes from the queue per atomic (tiny rows: the queue head would serialise the launch)
+    int32_t sort_max;          // FILL: leave a work item's segment of the pair list sorted by pair class (see pair_class) when it has at
+                               // most this many pairs (0: never; SORT_K x the smallest CTA of the pass: a thread keeps its pairs in registers)
     int32_t split8;            // NUMERIC: 8 lanes per surviving pair, one per row of the A block (blocks with >= 4 values: a lane
                                // that multiplies a whole pair alone walks up to 64 x 8 dependent loads)
     int32_t group;             // consecutive block rows per work item (1..32): tiny rows are processed a group at a time -- one bit set, one
@@ -255,7 +257,7 @@ __device__ __forceinline__ float inline_val(const uint4& v, int k) {
 }
 
 template <int MODE>
-__device__ __forceinline__ void apply_pair(const GemmArgs& g, const RowCtx& r, int a, const PairIn& in, int arow = -1, int rpl = 1) {
+__device__ __forceinline__ void apply_pair(const GemmArgs& g, const RowCtx& r, int a, const PairIn& in, int arow = -1) {
     const uint4 pm = in.pm;
     const uint64_t abmp = in.abmp, bbmp = ((uint64_t)pm.y << 32) | pm.x;
     const int rl = local_row(r.abr, r.nr, a);
@@ -277,10 +279,9 @@ __device__ __forceinline__ void apply_pair(const GemmArgs& g, const RowCtx& r, i
         else { cb = g.c_bmps[r.c0 + c]; dst = g.c_val + g.c_off[r.c0 + c]; }
         uint64_t rem = abmp;
         int ka = 0;
-        if (arow >= 0) {                                    // this lane's rows of the A block only: rows arow * rpl .. + rpl - 1
-            const int sh = 8 * rpl * arow;
-            rem = abmp & ((~0ull << (64 - 8 * rpl)) >> sh);
-            ka = sh ? __popcll(abmp >> (64 - sh)) : 0;
+        if (arow >= 0) {                                    // this lane's row of the A block only
+            rem = abmp & (0xFF00000000000000ull >> (8 * arow));
+            ka = arow ? __popcll(abmp >> (64 - 8 * arow)) : 0;
             if (!rem) return;
         }
         while (rem) {
@@ -300,9 +301,26 @@ __device__ __forceinline__ void apply_pair(const GemmArgs& g, const RowCtx& r, i
     }
 }
 
+// ---- pair classes (scalar NUMERIC pass with several lanes per pair) ---------------------------------------------------------------
+// The lanes of a warp walk their pairs in lockstep, so a warp takes as long as its slowest lane: on a stencil product the four pairs
+// of a warp mix tridiagonal x tridiagonal blocks (9 products per lane) with diagonal x diagonal ones (1) and single-value A blocks
+// (7 of 8 lanes idle) -- ncu showed ~4 active threads per instruction in the product loops.  FILL, which touches every pair's two
+// bitmaps anyway, therefore leaves a work item's segment of the pair list sorted by class: classes 0..8 = A blocks with more than two
+// values, ordered by (values per row of A) x (values per row of B) descending; classes 9..11 = A blocks with one or two values (top bit
+// of the entry's A index set): NUMERIC gives those ONE lane per pair instead of eight.
+constexpr int PAIR_CLASSES = 12, PAIR_LIGHT = 9, SORT_K = 4;
+constexpr uint32_t PAIR_LIGHT_FLAG = 0x80000000u;
+__device__ __forceinline__ int pair_class(uint64_t abmp, uint64_t bbmp) {
+    const int pa = __popcll(abmp), pb = __popcll(bbmp);
+    const int cb = min(3, (pb + 7) >> 3);                       // 1..3
+    if (pa <= 2) return PAIR_LIGHT + (3 - cb);
+    const int ca = min(3, (pa + 7) >> 3);
+    return 8 - ((ca - 1) * 3 + (cb - 1));
+}
+
 template <int MODE>
-__device__ __forceinline__ void process_pair(const GemmArgs& g, const RowCtx& r, int a, int b, int arow = -1, int rpl = 1) {
-    apply_pair<MODE>(g, r, a, load_pair<MODE>(g, a, b), arow, rpl);
+__device__ __forceinline__ void process_pair(const GemmArgs& g, const RowCtx& r, int a, int b, int arow = -1) {
+    apply_pair<MODE>(g, r, a, load_pair<MODE>(g, a, b), arow);
 }
 
 // ---- tensor-core path (dense blocks) -----------------------------------------------------------------
@@ -698,6 +716,8 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
     uint32_t* s_rsurv = reinterpret_cast<uint32_t*>(s_cbr + 33);   // [32]
     uint32_t* s_rowoff = s_rsurv + 32;                 // [33]
     if (tid == 0) { s_batch[0] = 0; s_batch[1] = 0; }
+    __shared__ uint32_t s_cls[PAIR_CLASSES];           // FILL: pairs per class of the work item (zero between work items)
+    if (tid < PAIR_CLASSES) s_cls[tid] = 0;
 
     unsigned long long n_cand = 0, n_surv_total = 0;
     int my_max1 = 0, my_max2 = 0, my_max3 = 0;         // per-thread maxima, published once when the CTA retires
@@ -812,7 +832,43 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
             }
             __syncthreads();
             rank_words(r.bitset, r.wrank, nwords, s_tmp);
-            for (uint32_t e = tid; e < nsurv; e += T) { const uint2 pr = list[e]; process_pair<MODE_FILL>(g, r, (int)pr.x, (int)pr.y); }
+            if (nsurv <= (uint32_t)g.sort_max) {
+                // apply the pairs and leave the segment sorted by class for NUMERIC (counting sort through shared counters; a thread
+                // keeps its <= SORT_K pairs in registers between reading and rewriting the segment)
+                uint2 mine[SORT_K]; uint32_t slot[SORT_K];
+#pragma unroll
+                for (int k = 0; k < SORT_K; k++) {
+                    const uint32_t e = tid + (uint32_t)k * T;
+                    slot[k] = 0xFFFFFFFFu;
+                    if (e < nsurv) {
+                        const uint2 pr = list[e];
+                        const PairIn in = load_pair<MODE_FILL>(g, (int)pr.x, (int)pr.y);
+                        apply_pair<MODE_FILL>(g, r, (int)pr.x, in);
+                        const int cls = pair_class(in.abmp, ((uint64_t)in.pm.y << 32) | in.pm.x);
+                        mine[k] = pr;
+                        slot[k] = ((uint32_t)cls << 24) | atomicAdd(&s_cls[cls], 1u);
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t run = 0;
+                    for (int c = 0; c < PAIR_CLASSES; c++) { const uint32_t t = s_cls[c]; s_cls[c] = run; run += t; }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < SORT_K; k++) {
+                    if (slot[k] != 0xFFFFFFFFu) {
+                        const uint32_t cls = slot[k] >> 24;
+                        uint2 pr = mine[k];
+                        if (cls >= (uint32_t)PAIR_LIGHT) pr.x |= PAIR_LIGHT_FLAG;
+                        list[s_cls[cls] + (slot[k] & 0xFFFFFFu)] = pr;
+                    }
+                }
+                __syncthreads();
+                if (tid < PAIR_CLASSES) s_cls[tid] = 0;
+            } else {
+                for (uint32_t e = tid; e < nsurv; e += T) { const uint2 pr = list[e]; process_pair<MODE_FILL>(g, r, (int)pr.x, (int)pr.y); }
+            }
             }
             __syncthreads();
             // keys, bitmaps and the derived per-block arrays out: ascending (row, bit index) = ascending key
@@ -871,12 +927,17 @@ __global__ void __launch_bounds__(MAXT) spgemm_pass_kernel(GemmArgs g) {
                 uint32_t ns = 0;
                 enumerate_fine<2, false>(g, r, ns);
             } else if (PASS == PASS_NUMERIC) {
-                if (g.split8 == 8) {
-                    for (uint64_t e = tid; e < (uint64_t)nsurv * 8u; e += T) { const uint2 pr = list[e >> 3]; process_pair<MODE_NUMERIC>(g, r, (int)pr.x, (int)pr.y, (int)(e & 7u)); }
-                } else if (g.split8 == 4) {             // four lanes per pair, two rows of the A block each
-                    for (uint64_t e = tid; e < (uint64_t)nsurv * 4u; e += T) { const uint2 pr = list[e >> 2]; process_pair<MODE_NUMERIC>(g, r, (int)pr.x, (int)pr.y, (int)(e & 3u), 2); }
-                } else if (g.split8 == 2) {
-                    for (uint64_t e = tid; e < (uint64_t)nsurv * 2u; e += T) { const uint2 pr = list[e >> 1]; process_pair<MODE_NUMERIC>(g, r, (int)pr.x, (int)pr.y, (int)(e & 1u), 4); }
+                if (g.split8) {
+                    // the segment is sorted by class (FILL): h pairs with eight lanes each -- one per row of the A block --, then the
+                    // pairs whose A block has one or two values, one lane each.  An unsorted segment (too many pairs for FILL's
+                    // registers) carries no flags: h = nsurv.
+                    uint32_t h = nsurv;
+                    if (nsurv <= (uint32_t)g.sort_max) {
+                        h = 0;
+                        for (uint32_t e0 = 0; e0 < nsurv; e0 += T) h += (uint32_t)__syncthreads_count(e0 + tid < nsurv && !(list[e0 + tid].x & PAIR_LIGHT_FLAG));
+                    }
+                    for (uint64_t e = tid; e < (uint64_t)h * 8u; e += T) { const uint2 pr = list[e >> 3]; process_pair<MODE_NUMERIC>(g, r, (int)(pr.x & ~PAIR_LIGHT_FLAG), (int)pr.y, (int)(e & 7u)); }
+                    for (uint32_t e = h + tid; e < nsurv; e += T) { const uint2 pr = list[e]; process_pair<MODE_NUMERIC>(g, r, (int)(pr.x & ~PAIR_LIGHT_FLAG), (int)pr.y); }
                 } else if (MAXT == 1024) {            // 32 registers per thread: one pair at a time
                     for (uint32_t e = tid; e < nsurv; e += T) { const uint2 pr = list[e]; process_pair<MODE_NUMERIC>(g, r, (int)pr.x, (int)pr.y); }
                 } else {
@@ -1308,8 +1369,15 @@ extern "C" int bmsp_spgemm(bmsp_matrix_t A, bmsp_matrix_t Bt, const bmsp_spgemm_
     g.rowinfo = rowinfo; g.row_begin = rb; g.row_end = re; g.G = G;
     // P4096 A*A: 2.1 M block rows of 25 candidate pairs -- one atomic on the queue head per row and pass cost more than the rows
     g.group = group;
-    static const int split_env = [] { const char* e = getenv("BMSP_SPGEMM_SPLIT"); const int v = e ? atoi(e) : 8; return (v == 2 || v == 4 || v == 8) ? v : 8; }();
-    g.split8 = (A->nblk > 0 && (double)A->nnz / (double)A->nblk >= 4.0) ? split_env : 0;
+    // (four / two lanes per pair with two / four rows each were measured on P4096: NUMERIC 8.35 / 8.97 ms against 7.45 ms with eight)
+    g.split8 = A->nblk > 0 && (double)A->nnz / (double)A->nblk >= 4.0;
+    {   // FILL sorts its pair-list segments by class only for the pass that reads them: the scalar NUMERIC pass with 8 lanes per pair
+        const double dA0 = A->nblk ? (double)A->nnz / A->nblk : 0.0, dB0 = Bt->nblk ? (double)Bt->nnz / Bt->nblk : 0.0;
+        int path0 = opts ? opts->numeric_path : -1;
+        if (path0 < 0) path0 = (dA0 * dB0 / 8.0 >= 40.0) ? 1 : 0;
+        static const int sort_env = [] { const char* e = getenv("BMSP_SPGEMM_SORT"); return e ? atoi(e) : 1; }();
+        g.sort_max = (g.split8 && path0 == 0 && sort_env) ? SORT_K * T : 0;
+    }
     g.batch = group > 1 ? 2 : (avg_cand <= 96 ? 32 : (avg_cand <= 2048 ? 4 : 1));
     g.cap_words = (int64_t)group * max_words <= 8192 ? std::max(1, group * max_words) : (avg_words > 4096.0 ? 256 : 8192);
     g.cap_c = 0; g.cap_nnz = 0;
