@@ -32,6 +32,18 @@ def split_by_weight(weights: np.ndarray, nparts: int, align: int = 1) -> np.ndar
     return bounds
 
 
+def deal_chunks(nchunks: int, world: int, rank: int) -> list:
+    """Which of `nchunks` work chunks (ordered from the heaviest rows to the lightest) rank `rank` of `world` takes: rounds of
+    `world` chunks, every other round in reverse rank order, so that no rank is handed the heavier chunk of every round (a plain
+    cyclic deal does that to rank 0).  Every chunk goes to exactly one rank; counts differ by at most one."""
+    mine = []
+    for rnd in range((nchunks + world - 1) // world):
+        c = rnd * world + (rank if rnd % 2 == 0 else world - 1 - rank)
+        if c < nchunks:
+            mine.append(c)
+    return mine
+
+
 def csr_row_slice(rp, ci, v, r0, r1):
     """rows [r0, r1) of a CSR triple, row_ptr rebased to 0 (columns untouched)."""
     s, e = int(rp[r0]), int(rp[r1])

@@ -83,6 +83,23 @@ def test_split_by_weight():
     assert np.all(split_by_weight(np.ones(64), 8, align=8) % 8 == 0)
 
 
+def test_deal_chunks_partitions_every_chunk_once():
+    """work chunks of the chunked SpGEMM: every chunk to exactly one rank, counts within one of each other, and the sum of a
+    decreasing cost sequence is better balanced than with a plain cyclic deal"""
+    from bmsparse_spgemm_spmv_b200.dist import deal_chunks
+    for world in (1, 2, 3, 4, 8):
+        for n in (0, 1, 7, 8, 21, 84, 88):
+            got = [deal_chunks(n, world, r) for r in range(world)]
+            flat = sorted(c for g in got for c in g)
+            assert flat == list(range(n))
+            sizes = [len(g) for g in got]
+            assert max(sizes) - min(sizes) <= 1
+    cost = np.linspace(2.0, 1.0, 84)
+    zig = [cost[deal_chunks(84, 4, r)].sum() for r in range(4)]
+    cyc = [cost[list(range(r, 84, 4))].sum() for r in range(4)]
+    assert max(zig) - min(zig) < max(cyc) - min(cyc)
+
+
 def test_halo_descriptor_layout():
     """The peer-memory halo plan (pure address arithmetic of dist.halo_descriptor): three slabs of a banded matrix.  Every push
     range starts on a multiple of 4 rows, lands 16-byte aligned inside the peer's x buffer at the row's position in the peer's

@@ -114,7 +114,8 @@ def rmat_spgemm(c: Ctx, A, Bt, rp, ci, chunk_pairs=3e9, max_chunks=0):
     # chunks dealt in rounds of N, every other round in reverse rank order: the hub rows sit in the first chunks and a hub chunk costs
     # more per candidate pair than a tail chunk, so contiguous ranges would leave rank 0 with the slowest ones, and a plain cyclic deal
     # still hands rank 0 the heavier chunk of every round
-    mine = [rnd * c.world + (c.rank if rnd % 2 == 0 else c.world - 1 - c.rank) for rnd in range(cpr)]
+    from bmsparse_spgemm_spmv_b200.dist import deal_chunks
+    mine = deal_chunks(c.world * cpr, c.world, c.rank)
     c.barrier()
     spent = 0.0; blocks = 0; nnz = 0; keysum = 0; valsum = 0.0; cand = 0; surv = 0; done = 0; err = None
     for ch in mine:
