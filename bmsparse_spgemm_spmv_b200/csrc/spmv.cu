@@ -880,6 +880,8 @@ __global__ void __launch_bounds__(NG * (32 + RTT * 2), MINB) spmv_stream_kernel(
                 if (part || (nb > 0 && ((int64_t)d1.z * 32 < hd.own_c0 || ((int64_t)d1.w + 1) * 32 > hd.own_c1))) {
                     halo_wait_all(&hd, lane, !staged);
                     __syncwarp();
+                    // the x lines are fetched by the async proxy (bulk copies): order them behind the acquire made above
+                    asm volatile("fence.proxy.async;" ::: "memory");
                 }
             }
             // everything above is ready before the stage is: what follows the wait is the stage's critical path (a group has two
