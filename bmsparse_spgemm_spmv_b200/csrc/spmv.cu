@@ -1341,6 +1341,7 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, 
                 if (!A->spmv_sched) {
                     BMSP_TRY(dev_alloc_t(&A->spmv_sched, (size_t)SCHED_SLOTS * 2, st));
                     BMSP_CUDA(cudaMemsetAsync(A->spmv_sched, 0, sizeof(int32_t) * SCHED_SLOTS * 2, st));
+                    BMSP_CUDA(cudaStreamSynchronize(st));      // once per matrix: a launch on another stream must not see the counters unset
                 }
                 sched = A->spmv_sched + 2 * (A->spmv_sched_next++ % SCHED_SLOTS);
             }
