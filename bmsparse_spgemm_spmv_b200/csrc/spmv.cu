@@ -1191,6 +1191,12 @@ static int plan_tiles(bmsp_matrix_s* m, cudaStream_t st) {
     BMSP_KERNEL_CHECK();
     BMSP_TRY(dev_alloc_t(&stats, 8, st));
     BMSP_CUDA(cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), st));
+    if (m->spmv_kernel == 0 && !m->spmv_sched) {
+        // tile-claim counters of the streaming kernel (zero before the plan's synchronisation below, so that no later launch -- on
+        // whatever stream, captured in a graph or not -- has to wait for them)
+        BMSP_TRY(dev_alloc_t(&m->spmv_sched, (size_t)SCHED_SLOTS * 2, st));
+        BMSP_CUDA(cudaMemsetAsync(m->spmv_sched, 0, sizeof(int32_t) * SCHED_SLOTS * 2, st));
+    }
     tile_plan_kernel<<<ntiles, 256, 0, st>>>(m->brp, m->bcol, m->rvb, m->nbr, m->cols, rt, m->xl_pitch, (TileDesc*)m->tile_desc, m->tile_lines, m->tile_xoff, stats);
     BMSP_KERNEL_CHECK();
     unsigned long long h[8];
@@ -1338,12 +1344,7 @@ static int launch_spmv(bmsp_matrix_s* A, const X* x, float* y, cudaStream_t st, 
             // they must not share a counter); launches over a tile range (the host-buffer pipeline's chunks) keep static shares.
             int32_t* sched = nullptr;
             if (ntiles < 0 && tile_list == nullptr) {
-                if (!A->spmv_sched) {
-                    BMSP_TRY(dev_alloc_t(&A->spmv_sched, (size_t)SCHED_SLOTS * 2, st));
-                    BMSP_CUDA(cudaMemsetAsync(A->spmv_sched, 0, sizeof(int32_t) * SCHED_SLOTS * 2, st));
-                    BMSP_CUDA(cudaStreamSynchronize(st));      // once per matrix: a launch on another stream must not see the counters unset
-                }
-                sched = A->spmv_sched + 2 * (A->spmv_sched_next++ % SCHED_SLOTS);
+                if (A->spmv_sched) sched = A->spmv_sched + 2 * (A->spmv_sched_next++ % SCHED_SLOTS);      // allocated and zeroed by the plan
             }
             if (rt == 128) return launch_stream_kernel<T, X, 128, 1, 3, H>(a, x, y, hd, grid, st, sched);
             if (rt == 32) return launch_stream_kernel<T, X, 32, 1, 8, H>(a, x, y, hd, grid, st, sched);
