@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session a: tests + A/B of the SpMV tile kernel (round-1 library vs tridiagonal fast path) + ncu capture
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r2a_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2a_pytest.log
 L=bmsparse_spgemm_spmv_b200/lib

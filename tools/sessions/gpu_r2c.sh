@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session c: streaming SpMV kernel after the producer / stage-ownership fixes
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2c_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2c_pytest.log
 tail -5 gpurun_out/r2c_pytest.log

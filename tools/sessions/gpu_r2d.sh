@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session d: streaming SpMV kernel with one producer warp per group -- geometry sweep
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_spmv.py tests/test_gpu_cpp_shim.py -x -q > gpurun_out/r2d_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2d_pytest.log
 tail -5 gpurun_out/r2d_pytest.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session e: full GPU test suite (incl. full-size parity), SpMV sweep, ncu capture, the new bench line
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 ( time timeout 1500 python -m pytest tests -m gpu -x -q --durations=12 ) > gpurun_out/r2e_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2e_pytest.log
 tail -25 gpurun_out/r2e_pytest.log

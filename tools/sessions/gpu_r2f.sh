@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session f (2 GPUs): multi-GPU parity tests + the bench line at N = 2
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 python tools/spmv_bench.py p4096 300 2>&1 | tail -1 > gpurun_out/r2f_spmv.log
 python tools/spmv_bench.py p2048 300 2>&1 | tail -1 >> gpurun_out/r2f_spmv.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session g (2 GPUs): R-MAT-22 SpMV strong scaling with coalesced peer stores, halo step overhead
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 python tools/rmat_scale.py --what spmv,poisson --steps 100 > gpurun_out/r2g_rmat_n1.json 2> gpurun_out/r2g.err

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session h (1 GPU): new boundary / export tests, halo code-path self-test, final ncu capture of the streaming kernel
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 ( time timeout 900 python -m pytest tests/test_gpu_convert.py tests/test_gpu_cpp_shim.py tests/test_gpu_spmv.py -x -q ) > gpurun_out/r2h_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2h_pytest.log
 tail -15 gpurun_out/r2h_pytest.log

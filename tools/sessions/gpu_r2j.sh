@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session j (1 GPU): SpGEMM through B's fine index; halo variant of the streaming kernel with its multi-GPU code out of line
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 ( time timeout 900 python -m pytest tests/test_gpu_spgemm.py tests/test_gpu_reference_cuda.py tests/test_gpu_fullsize.py -x -q ) > gpurun_out/r2j_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2j_pytest.log
 tail -6 gpurun_out/r2j_pytest.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session l (1 GPU): fine index second walk, dense kernel with column windows, halo tile intervals
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 ( time timeout 900 python -m pytest tests/test_gpu_spgemm.py tests/test_gpu_reference_cuda.py tests/test_gpu_fullsize.py -x -q ) > gpurun_out/r2l_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2l_pytest.log
 tail -6 gpurun_out/r2l_pytest.log

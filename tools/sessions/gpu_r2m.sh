@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session m (2 GPUs): split halo launch (boundary / interior), block-parallel halo by push kernel
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 python tools/halo_selftest.py 300 2>&1 | tail -1 | tee gpurun_out/r2m_halo.log

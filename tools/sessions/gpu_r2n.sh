@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session n (1 GPU): CTA size of the fine-index passes, halo variant with its rare actions out of line, full test suite
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 python tools/halo_selftest.py 300 2>&1 | tail -1 | tee gpurun_out/r2n_halo.log
 r() { echo "== $*" >> gpurun_out/r2n_spgemm.log; env "${@:2}" python tools/spgemm_bench.py $1 --reps 2 2>&1 | tail -1 >> gpurun_out/r2n_spgemm.log; }

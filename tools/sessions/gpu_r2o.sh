@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session o (2 GPUs): concurrent boundary launch, bundles of short block rows in the block-parallel SpMV
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 python tools/halo_selftest.py 300 2>&1 | tail -1 | tee gpurun_out/r2o_halo.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session q (2 GPUs): tile index through the stage header; bundles at N = 2; weak scaling
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 python tools/spmv_bench.py p4096 300 2>&1 | tail -1 | tee gpurun_out/r2q_spmv.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session r (1 GPU): producer work ahead of the stage wait; ncu captures for profiles/ (U1M passes, BC4M dense pass, launch list)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 python tools/spmv_bench.py p4096 300 2>&1 | tail -1 | tee gpurun_out/r2r_spmv.log
 python tools/spmv_bench.py p2048 300 2>&1 | tail -1 | tee -a gpurun_out/r2r_spmv.log

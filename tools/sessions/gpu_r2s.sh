@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session s (2 GPUs): halo path with one fence per pushing tile + acquire-load waits; bundle test; N = 2 bench with the strong section
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 python tools/halo_selftest.py 300 2>&1 | tail -1 | tee gpurun_out/r2s_halo.log

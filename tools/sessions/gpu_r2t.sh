@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session t (1 GPU): tiles claimed at run time -- share of dynamically claimed tiles 0 / 25 / 50 / 100 %, plain and halo variant
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 : > gpurun_out/r2t.log
 for d in 0 25 50 100; do

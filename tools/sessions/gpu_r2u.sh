@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session u (1 GPU): share of claimed tiles 12 / 18 / 25 / 33 %; conversion with the chunk-row table
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 : > gpurun_out/r2u.log
 for d in 12 18 25 33; do

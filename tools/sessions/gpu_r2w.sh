@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 session w (N GPUs): measured-cost split of the R-MAT-22 SpMV, warp-per-row fix-up; usage: bash tools/gpu_r2w.sh N
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 N=${1:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"

@@ -1,6 +1,7 @@
 #!/bin/bash
 # round-2 session z (1 GPU): lanes per surviving pair in the scalar NUMERIC pass (8 / 4 / 2) on the stencil configs
-cd "$(dirname "$0")/.."
+# (BMSP_SPGEMM_SPLIT, used below, was an experiment switch removed after this session: eight lanes per pair stayed)
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 : > gpurun_out/r2z.log
 for s in 8 4 2; do
